@@ -1,0 +1,192 @@
+/*
+ * irl_maxent_b200.h -- C ABI of libirlmaxent_b200.so
+ *
+ * B200-native (sm_100a) replacement for the arithmetic behind the MaxEnt /
+ * MaxCausalEnt IRL hot path of narendasan/irl-maxent.  The reference has no FFI
+ * layer -- its boundary is a set of Python functions on dense numpy arrays
+ * (src/maxent.py, src/solver.py).  Each entry point below names the reference
+ * function (file:line under /root/reference) whose arithmetic it replaces; the
+ * ctypes stub a maintainer of the reference would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer unless its name starts with `h_`.
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  All
+ *     work is enqueued on it; nothing synchronises the host unless documented.
+ *   - Every function returns 0 on success, a negative IRLB200_E* code otherwise;
+ *     irlb200_last_error() gives a message for the calling thread.
+ *   - Values are IEEE float64 (the reference computes in float64 only);
+ *     indices are int32 (S < 2^31).
+ *   - There is NO CPU fallback: without a CUDA device every compute entry
+ *     point returns IRLB200_ECUDA.
+ *
+ * Table layout ("state-merged ELL", slot-major so that threads mapped to
+ * consecutive states read consecutive addresses):
+ *   successors   succ_idx[K][S]  int32    j-th distinct successor of state s
+ *                succ_p  [A][K][S] f64    P[s, succ_idx[j][s], a]
+ *   predecessors pred_idx[K][S]  int32    j-th distinct predecessor of state s'
+ *                pred_p  [A][K][S] f64    P[pred_idx[j][s'], s', a]
+ *   Slots hold the distinct neighbours in ascending state order; unused slots
+ *   are padded with idx = own state, p = 0.  K is discovered from the data
+ *   (irlb200_dense_count), not assumed.
+ *   A batch of B problems stores B such tables back to back (`table_stride`
+ *   elements apart, counted in states*slots, see each call); stride 0 shares
+ *   one table between all problems of the batch.
+ */
+#ifndef IRL_MAXENT_B200_H
+#define IRL_MAXENT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IRLB200_OK        0
+#define IRLB200_EINVAL   (-1)   /* bad argument (shape, null pointer, unsupported size) */
+#define IRLB200_ECUDA    (-2)   /* CUDA runtime error / no device */
+#define IRLB200_ELIMIT   (-3)   /* problem does not fit the requested execution mode */
+
+/* status bits written to `status` outputs by the sweep kernels */
+#define IRLB200_ST_CONVERGED   0   /* stopped because delta <= eps (or fixed count reached) */
+#define IRLB200_ST_NONFINITE   1   /* stopped because delta was NaN (reference: NaN ends the loop) */
+#define IRLB200_ST_MAXSWEEPS   2   /* stopped by the max_sweeps guard (reference would keep looping) */
+
+/* execution modes for a single problem (batched calls always use IRLB200_MODE_CTA) */
+#define IRLB200_MODE_AUTO     0
+#define IRLB200_MODE_CTA      1   /* one CTA owns the problem: iterate in shared memory      */
+#define IRLB200_MODE_CLUSTER  2   /* one thread-block cluster owns it: iterate in DSMEM      */
+#define IRLB200_MODE_GRID     3   /* cooperative persistent grid: iterate in L2/HBM          */
+
+int         irlb200_version(void);
+const char *irlb200_last_error(void);
+/* number of CUDA devices visible to the library (0 => every compute call fails) */
+int         irlb200_device_count(void);
+/* limits of the execution modes on the current device */
+int         irlb200_max_states_cta(void);
+int         irlb200_max_states_cluster(void);
+
+/* ------------------------------------------------------------------------- *
+ * (1) one-time compression of the dense table
+ *     replaces the per-call dense slicing `[np.array(p_transition[:, :, a]) ...]`
+ *     maxent.py:102,143,320 and solver.py:37, and the copy+mask maxent.py:98-99.
+ * ------------------------------------------------------------------------- */
+
+/* Pass 1: count distinct successors / predecessors of every state.
+ *   P        [S][S][A] f64, C-contiguous (A innermost: gridworld.py:124-142)
+ *   succ_cnt [S] int32 out, pred_cnt [S] int32 out
+ *   kmax     [2] int32 out: {max succ_cnt, max pred_cnt}                     */
+int irlb200_dense_count(const double *P, int S, int A,
+                        int32_t *succ_cnt, int32_t *pred_cnt, int32_t *kmax, void *stream);
+
+/* Pass 2: fill the tables (layout above) for slot counts Ks >= kmax[0], Kp >= kmax[1].
+ *   pred_cnt is consumed as scratch (must hold the pass-1 values, returns them unchanged). */
+int irlb200_dense_fill(const double *P, int S, int A, int Ks, int Kp,
+                       int32_t *succ_idx, double *succ_p,
+                       int32_t *pred_idx, double *pred_p,
+                       int32_t *pred_cnt, void *stream);
+
+/* Tables of GridWorld / IcyGridWorld built directly, no dense detour
+ *   (gridworld.py:144-171 deterministic when icy == 0, :200-248 icy otherwise).
+ *   Ks = Kp = 5.  B worlds with per-world slip probability p_slip[b] (device, f64);
+ *   tables of world b start at element b * (5*S) of the idx arrays and
+ *   b * (A*5*S) of the p arrays.  Values are bit-identical to the reference's. */
+int irlb200_gridworld_tables(int size, int icy, int B, const double *p_slip,
+                             int32_t *succ_idx, double *succ_p,
+                             int32_t *pred_idx, double *pred_p, void *stream);
+
+/* Dense P[S][S][A] of the same worlds, written on the device (test helper for the
+ * compression kernels at sizes where the Python table builder is too slow). */
+int irlb200_gridworld_dense(int size, int icy, double p_slip, double *P, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Problem descriptor shared by the sweep entry points
+ * ------------------------------------------------------------------------- */
+typedef struct irlb200_tables {
+    int32_t S, A;             /* states, actions                                         */
+    int32_t Ks, Kp;           /* slots per state in the successor / predecessor table    */
+    const int32_t *succ_idx;  /* [B or 1][Ks][S]                                          */
+    const double  *succ_p;    /* [B or 1][A][Ks][S]                                       */
+    const int32_t *pred_idx;  /* [B or 1][Kp][S]                                          */
+    const double  *pred_p;    /* [B or 1][A][Kp][S]                                       */
+    int32_t shared;           /* 1: one table for the whole batch, 0: one table per problem */
+} irlb200_tables;
+
+/* ------------------------------------------------------------------------- *
+ * (2) non-causal backward pass -- local_action_probabilities, maxent.py:119-159
+ *     fused: exp(reward) (:142), n_sweeps partition sweeps (:154-156, the
+ *     reference uses 2*S), action normalisation (:159).  Range-extended by an
+ *     exact power-of-two rescale (bit-identical to the raw loop where that is
+ *     finite).
+ *   reward   [B][S]          terminal_mask [B or 1][S] uint8 (1 = terminal; zs seed :146-147)
+ *   policy   [B][S][A] out
+ * ------------------------------------------------------------------------- */
+int irlb200_backward(const irlb200_tables *t, int B, const double *reward,
+                     const uint8_t *terminal_mask, int mask_shared, int n_sweeps,
+                     double *policy, int mode, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * (3) causal soft value iteration -- local_causal_action_probabilities,
+ *     maxent.py:279-341 (softmax fold :260-276, -1e200 start :323, policy :341)
+ *   phi [B or 1][S] terminal reward function (0 at terminals, -inf elsewhere, or
+ *       the caller's array, :312-317)
+ *   policy [B][S][A] out, n_iter [B] int32 out, status [B] int32 out
+ *   max_sweeps <= 0 means no guard (the reference has none).
+ * ------------------------------------------------------------------------- */
+int irlb200_soft_vi(const irlb200_tables *t, int B, const double *reward,
+                    const double *phi, int phi_shared, double discount, double eps,
+                    int max_sweeps, double *policy, double *value_out /* [B][S] or NULL */,
+                    int32_t *n_iter, int32_t *status, int mode, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * value iteration -- solver.value_iteration, solver.py:9-52
+ *   kind 0: max over actions (:47); kind 1: mean over actions
+ *   (stochastic_value_iteration, solver.py:55-104)
+ * ------------------------------------------------------------------------- */
+int irlb200_value_iteration(const irlb200_tables *t, int B, const double *reward,
+                            double discount, double eps, int max_sweeps, int kind,
+                            double *value, int32_t *n_iter, int32_t *status,
+                            int mode, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * (4) forward state-visitation pass -- expected_svf_from_policy, maxent.py:63-114
+ *     gather over predecessors; the outgoing rows of terminal states are
+ *     dropped (:98-99) through the mask; per-policy predecessor weights
+ *     W[j][s'] = sum_a P[s_j,s',a] * policy[s_j,a] are formed on chip.
+ *   p_initial [B or 1][S], policy [B][S][A], svf [B][S] out
+ *   grad      [B][S] out or NULL: fused epilogue for identity features,
+ *             grad = e_features - svf   (maxent.py:248 with features = I)
+ * ------------------------------------------------------------------------- */
+int irlb200_svf(const irlb200_tables *t, int B, const double *p_initial, int p0_shared,
+                const uint8_t *terminal_mask, int mask_shared, const double *policy,
+                double eps, int max_sweeps,
+                double *svf, const double *e_features, double *grad,
+                int32_t *n_iter, int32_t *status, int mode, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * fused gradient step: (2)+(4) or (3)+(4) in ONE launch per batch --
+ * compute_expected_svf maxent.py:162-193 / compute_expected_causal_svf :344-380,
+ * the policy never leaves the SM.  causal == 0: backward pass with n_backward
+ * sweeps; causal != 0: soft-VI with (discount, eps_lap).
+ *   n_iter [B][2] int32 out: {policy sweeps, svf sweeps};  status [B][2]
+ * ------------------------------------------------------------------------- */
+int irlb200_expected_svf(const irlb200_tables *t, int B, int causal,
+                         const double *reward, const double *p_initial, int p0_shared,
+                         const uint8_t *terminal_mask, const double *phi, int mask_shared,
+                         int n_backward, double discount, double eps_lap, double eps_svf,
+                         int max_sweeps, double *svf, const double *e_features, double *grad,
+                         double *policy_out /* [B][S][A] or NULL */,
+                         int32_t *n_iter, int32_t *status, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * dense feature products on the path: reward = features . theta (maxent.py:244)
+ * and grad = e_features - features^T . svf (:248).  features [S][F] row-major.
+ * ------------------------------------------------------------------------- */
+int irlb200_features_dot(const double *features, int S, int F, const double *theta,
+                         double *reward, void *stream);
+int irlb200_features_grad(const double *features, int S, int F, const double *svf,
+                          const double *e_features, double *grad, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IRL_MAXENT_B200_H */

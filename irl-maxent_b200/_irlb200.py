@@ -1,0 +1,493 @@
+"""
+_irlb200 -- host-side engine: ctypes binding of libirlmaxent_b200.so (the C ABI
+declared in include/irl_maxent_b200.h) plus the device-resident table handle.
+
+PyTorch is used for plumbing only (device memory, streams, host<->device
+copies); every arithmetic step of the hot path runs in the hand-written
+sm_100a kernels behind the C ABI.  There is NO CPU fallback: if the shared
+library is missing or no CUDA device is visible, every compute call raises.
+"""
+
+import ctypes
+import os
+import weakref
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libirlmaxent_b200.so")
+
+MODE_AUTO, MODE_CTA, MODE_CLUSTER, MODE_GRID = 0, 1, 2, 3
+ST_CONVERGED, ST_NONFINITE, ST_MAXSWEEPS = 0, 1, 2
+
+# guard against inputs for which the reference would loop forever
+# (non-absorbing policies, maxent.py:108); 0 disables the guard
+DEFAULT_MAX_SWEEPS = int(os.environ.get("IRLB200_MAX_SWEEPS", "200000000"))
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class _CTables(ctypes.Structure):
+    _fields_ = [("S", ctypes.c_int32), ("A", ctypes.c_int32),
+                ("Ks", ctypes.c_int32), ("Kp", ctypes.c_int32),
+                ("succ_idx", ctypes.c_void_p), ("succ_p", ctypes.c_void_p),
+                ("pred_idx", ctypes.c_void_p), ("pred_p", ctypes.c_void_p),
+                ("shared", ctypes.c_int32)]
+
+
+_lib = None
+
+_vp, _i, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+_tp = ctypes.POINTER(_CTables)
+
+# name -> argtypes; mirrors include/irl_maxent_b200.h one to one
+SIGNATURES = {
+    "irlb200_version": ([], _i),
+    "irlb200_last_error": ([], ctypes.c_char_p),
+    "irlb200_device_count": ([], _i),
+    "irlb200_max_states_cta": ([], _i),
+    "irlb200_max_states_cluster": ([], _i),
+    "irlb200_dense_count": ([_vp, _i, _i, _vp, _vp, _vp, _vp], _i),
+    "irlb200_dense_fill": ([_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "irlb200_gridworld_tables": ([_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "irlb200_gridworld_dense": ([_i, _i, _d, _vp, _vp], _i),
+    "irlb200_backward": ([_tp, _i, _vp, _vp, _i, _i, _vp, _i, _vp], _i),
+    "irlb200_soft_vi": ([_tp, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _i, _vp], _i),
+    "irlb200_value_iteration": ([_tp, _i, _vp, _d, _d, _i, _i, _vp, _vp, _vp, _i, _vp], _i),
+    "irlb200_svf": ([_tp, _i, _vp, _i, _vp, _i, _vp, _d, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),
+    "irlb200_expected_svf": ([_tp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _d, _d, _d, _i,
+                              _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "irlb200_features_dot": ([_vp, _i, _i, _vp, _vp, _vp], _i),
+    "irlb200_features_grad": ([_vp, _i, _i, _vp, _vp, _vp, _vp], _i),
+}
+
+
+def load_library(path=None):
+    """dlopen the C-ABI library and declare every prototype.  No compute happens here."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise EngineError(
+            "native library %s is missing: build it with `python irl-maxent_b200/build_native.py` "
+            "(there is no CPU fallback)" % path)
+    lib = ctypes.CDLL(path)
+    for name, (argtypes, restype) in SIGNATURES.items():
+        fn = getattr(lib, name)         # AttributeError if the symbol is not exported
+        fn.argtypes, fn.restype = argtypes, restype
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise EngineError("libirlmaxent_b200: error %d: %s" % (rc, _lib.irlb200_last_error().decode()))
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def require_cuda():
+    torch = _torch()
+    lib = load_library()
+    if not torch.cuda.is_available() or lib.irlb200_device_count() <= 0:
+        raise EngineError("no CUDA device: the B200 engine has no CPU fallback")
+    return torch
+
+
+def _stream():
+    return ctypes.c_void_p(_torch().cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _dev():
+    return _torch().device("cuda", _torch().cuda.current_device())
+
+
+def to_device(x, dtype=None):
+    """numpy / list / tensor -> contiguous CUDA tensor (float64 unless dtype given)."""
+    torch = _torch()
+    dtype = dtype or torch.float64
+    if isinstance(x, torch.Tensor):
+        return x.to(device=_dev(), dtype=dtype).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(_dev())
+
+
+def is_tensor(x):
+    try:
+        import torch
+        return isinstance(x, torch.Tensor)
+    except ImportError:                                         # pragma: no cover
+        return False
+
+
+# ---------------------------------------------------------------------------
+# tables
+# ---------------------------------------------------------------------------
+
+class Tables:
+    """Device-resident state-merged ELL tables of B (or one shared) MDP(s).
+
+    Layout as in include/irl_maxent_b200.h: succ_idx [Bt][Ks][S] int32,
+    succ_p [Bt][A][Ks][S] f64, pred_idx [Bt][Kp][S], pred_p [Bt][A][Kp][S].
+    """
+
+    def __init__(self, S, A, Ks, Kp, succ_idx, succ_p, pred_idx, pred_p, n_tables=1):
+        self.S, self.A, self.Ks, self.Kp = int(S), int(A), int(Ks), int(Kp)
+        self.succ_idx, self.succ_p, self.pred_idx, self.pred_p = succ_idx, succ_p, pred_idx, pred_p
+        self.n_tables = int(n_tables)
+
+    # the reference's `n_states, _, n_actions = p_transition.shape` keeps working on a handle
+    @property
+    def shape(self):
+        return (self.S, self.S, self.A)
+
+    def c_struct(self, shared):
+        return _CTables(self.S, self.A, self.Ks, self.Kp, self.succ_idx.data_ptr(), self.succ_p.data_ptr(),
+                        self.pred_idx.data_ptr(), self.pred_p.data_ptr(), 1 if shared else 0)
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.succ_idx, self.succ_p, self.pred_idx, self.pred_p))
+
+    def select(self, b):
+        """Handle on the tables of world b of a batch (views, no copy)."""
+        return Tables(self.S, self.A, self.Ks, self.Kp, self.succ_idx[b:b + 1], self.succ_p[b:b + 1],
+                      self.pred_idx[b:b + 1], self.pred_p[b:b + 1], 1)
+
+
+def _round_slots(A, k):
+    # every 4-action table with <= 5 neighbours is padded to the register-resident shape
+    k = max(int(k), 1)
+    return 5 if (A == 4 and k <= 5) else k
+
+
+def compress_dense(p_transition):
+    """Kernel (1): dense p_transition[S,S',A] -> Tables (one-time)."""
+    torch = require_cuda()
+    P = to_device(p_transition)
+    if P.dim() != 3 or P.shape[0] != P.shape[1]:
+        raise EngineError("p_transition must have shape [S, S, A]")
+    S, A = int(P.shape[0]), int(P.shape[2])
+    dev = P.device
+    succ_cnt = torch.empty(S, dtype=torch.int32, device=dev)
+    pred_cnt = torch.empty(S, dtype=torch.int32, device=dev)
+    kmax = torch.empty(2, dtype=torch.int32, device=dev)
+    _check(_lib.irlb200_dense_count(_ptr(P), S, A, _ptr(succ_cnt), _ptr(pred_cnt), _ptr(kmax), _stream()))
+    ks, kp = (int(v) for v in kmax.tolist())            # host sync: sizes are needed to allocate
+    Ks, Kp = _round_slots(A, ks), _round_slots(A, kp)
+    succ_idx = torch.empty((1, Ks, S), dtype=torch.int32, device=dev)
+    succ_p = torch.empty((1, A, Ks, S), dtype=torch.float64, device=dev)
+    pred_idx = torch.empty((1, Kp, S), dtype=torch.int32, device=dev)
+    pred_p = torch.empty((1, A, Kp, S), dtype=torch.float64, device=dev)
+    _check(_lib.irlb200_dense_fill(_ptr(P), S, A, Ks, Kp, _ptr(succ_idx), _ptr(succ_p), _ptr(pred_idx),
+                                   _ptr(pred_p), _ptr(pred_cnt), _stream()))
+    t = Tables(S, A, Ks, Kp, succ_idx, succ_p, pred_idx, pred_p, 1)
+    t.k_discovered = (ks, kp)
+    return t
+
+
+def gridworld_tables(size, p_slip=None, icy=True):
+    """Tables of GridWorld / IcyGridWorld straight from (size, p_slip).
+    `p_slip` may be a scalar or a length-B sequence (B worlds)."""
+    torch = require_cuda()
+    if icy:
+        ps = np.atleast_1d(np.asarray(p_slip, dtype=np.float64))
+    else:
+        ps = np.zeros(1)
+    B = len(ps)
+    S, A, K = size * size, 4, 5
+    dev = _dev()
+    ps_d = to_device(ps)
+    succ_idx = torch.empty((B, K, S), dtype=torch.int32, device=dev)
+    succ_p = torch.empty((B, A, K, S), dtype=torch.float64, device=dev)
+    pred_idx = torch.empty((B, K, S), dtype=torch.int32, device=dev)
+    pred_p = torch.empty((B, A, K, S), dtype=torch.float64, device=dev)
+    _check(_lib.irlb200_gridworld_tables(size, 1 if icy else 0, B, _ptr(ps_d), _ptr(succ_idx), _ptr(succ_p),
+                                         _ptr(pred_idx), _ptr(pred_p), _stream()))
+    return Tables(S, A, K, K, succ_idx, succ_p, pred_idx, pred_p, B)
+
+
+def gridworld_dense(size, p_slip=0.2, icy=True):
+    """Dense [S,S,A] table of a grid world, built on the device (float64 CUDA tensor)."""
+    torch = require_cuda()
+    S = size * size
+    P = torch.empty((S, S, 4), dtype=torch.float64, device=_dev())
+    _check(_lib.irlb200_gridworld_dense(size, 1 if icy else 0, float(p_slip), _ptr(P), _stream()))
+    return P
+
+
+# ---- cache: the reference API hands the dense table to every call ------------
+
+_cache = {}
+
+
+def clear_cache():
+    _cache.clear()
+
+
+def as_tables(p_transition):
+    """Tables for whatever the caller passed as `p_transition` (dense array, CUDA
+    tensor or an existing handle).  Dense inputs are compressed once and cached by
+    object identity (small arrays additionally by content hash), because the
+    reference API passes the same dense table to every call of the inner loop."""
+    if isinstance(p_transition, Tables):
+        return p_transition
+    key = id(p_transition)
+    small = not is_tensor(p_transition) and getattr(p_transition, "nbytes", 1 << 62) <= (1 << 20)
+    digest = hash(np.ascontiguousarray(p_transition).tobytes()) if small else None
+    hit = _cache.get(key)
+    if hit is not None and hit[1] == digest and hit[2]() is p_transition:
+        return hit[0]
+    t = compress_dense(p_transition)
+    try:
+        ref = weakref.ref(p_transition, lambda _r, k=key: _cache.pop(k, None))
+    except TypeError:
+        return t
+    _cache[key] = (t, digest, ref)
+    return t
+
+
+# ---------------------------------------------------------------------------
+# helpers shared by the wrappers
+# ---------------------------------------------------------------------------
+
+def terminal_mask(terminal, S):
+    """uint8 [S] mask from an index collection (device)."""
+    torch = _torch()
+    m = np.zeros(S, dtype=np.uint8)
+    idx = np.asarray(list(terminal), dtype=np.int64)
+    if idx.size:
+        m[idx] = 1
+    return torch.as_tensor(m).to(_dev())
+
+
+def terminal_phi(terminal, S):
+    """maxent.py:312-317: the array itself iff len(terminal) == S, else 0 / -inf."""
+    if is_tensor(terminal):
+        if terminal.numel() == S:
+            return to_device(terminal)
+        terminal = terminal.tolist()
+    if len(terminal) == S:
+        return to_device(np.array(terminal, dtype=float))
+    phi = np.full(S, -np.inf)
+    phi[np.asarray(list(terminal), dtype=np.int64)] = 0.0
+    return to_device(phi)
+
+
+def _batch2d(x, S):
+    """[S] or [B,S] input -> (contiguous [B,S] device tensor, B)."""
+    t = to_device(x)
+    if t.dim() == 1:
+        t = t.unsqueeze(0)
+    if t.shape[-1] != S:
+        raise EngineError("expected trailing dimension %d, got %s" % (S, tuple(t.shape)))
+    return t.contiguous(), int(t.shape[0])
+
+
+def _tables_shared(tables, B):
+    if tables.n_tables == 1:
+        return True
+    if tables.n_tables != B:
+        raise EngineError("batch of %d problems needs 1 or %d tables, got %d" % (B, B, tables.n_tables))
+    return False
+
+
+def _maybe_shared(x, S, B, dtype=None):
+    """[S] (shared) or [B,S] per-problem vector -> (tensor, shared flag)."""
+    t = to_device(x, dtype)
+    if t.dim() == 1:
+        return t.contiguous(), 1
+    if t.shape[0] == 1 and B > 1:
+        return t[0].contiguous(), 1
+    if t.shape[0] != B:
+        raise EngineError("per-problem input has batch %d, expected %d" % (t.shape[0], B))
+    return t.contiguous(), 0
+
+
+class SweepInfo:
+    """Iteration counts / stop reasons of the last call (device tensors; reading
+    them synchronises)."""
+
+    def __init__(self, n_iter, status):
+        self.n_iter, self.status = n_iter, status
+
+    def counts(self):
+        return self.n_iter.cpu().numpy()
+
+    def stati(self):
+        return self.status.cpu().numpy()
+
+
+last_info = None
+
+
+# ---------------------------------------------------------------------------
+# entry-point wrappers (device tensors in, device tensors out)
+# ---------------------------------------------------------------------------
+
+def backward(tables, terminal_mask_t, reward, n_sweeps=None, mode=MODE_AUTO):
+    """(2) local_action_probabilities, maxent.py:119-159.  reward [S] or [B,S]."""
+    torch = require_cuda()
+    S, A = tables.S, tables.A
+    r, B = _batch2d(reward, S)
+    mask, mshared = _maybe_shared(terminal_mask_t, S, B, torch.uint8)
+    pol = torch.empty((B, S, A), dtype=torch.float64, device=r.device)
+    ct = tables.c_struct(_tables_shared(tables, B))
+    _check(_lib.irlb200_backward(ctypes.byref(ct), B, _ptr(r), _ptr(mask), mshared,
+                                 2 * S if n_sweeps is None else int(n_sweeps), _ptr(pol), mode, _stream()))
+    return pol
+
+
+def soft_vi(tables, phi, reward, discount, eps=1e-5, max_sweeps=None, mode=MODE_AUTO, want_value=False):
+    """(3) local_causal_action_probabilities, maxent.py:279-341."""
+    global last_info
+    torch = require_cuda()
+    S, A = tables.S, tables.A
+    r, B = _batch2d(reward, S)
+    ph, pshared = _maybe_shared(phi, S, B)
+    pol = torch.empty((B, S, A), dtype=torch.float64, device=r.device)
+    val = torch.empty((B, S), dtype=torch.float64, device=r.device) if want_value else None
+    n_iter = torch.zeros(B, dtype=torch.int32, device=r.device)
+    status = torch.zeros(B, dtype=torch.int32, device=r.device)
+    ct = tables.c_struct(_tables_shared(tables, B))
+    ms = DEFAULT_MAX_SWEEPS if max_sweeps is None else int(max_sweeps)
+    _check(_lib.irlb200_soft_vi(ctypes.byref(ct), B, _ptr(r), _ptr(ph), pshared, float(discount), float(eps),
+                                ms, _ptr(pol), _ptr(val), _ptr(n_iter), _ptr(status), mode, _stream()))
+    last_info = SweepInfo(n_iter, status)
+    return (pol, val) if want_value else pol
+
+
+def value_iteration(tables, reward, discount, eps=1e-3, max_sweeps=None, mean=False, mode=MODE_AUTO):
+    """solver.value_iteration, solver.py:9-52 (mean=True: :55-104)."""
+    global last_info
+    torch = require_cuda()
+    S = tables.S
+    r, B = _batch2d(reward, S)
+    val = torch.empty((B, S), dtype=torch.float64, device=r.device)
+    n_iter = torch.zeros(B, dtype=torch.int32, device=r.device)
+    status = torch.zeros(B, dtype=torch.int32, device=r.device)
+    ct = tables.c_struct(_tables_shared(tables, B))
+    ms = DEFAULT_MAX_SWEEPS if max_sweeps is None else int(max_sweeps)
+    _check(_lib.irlb200_value_iteration(ctypes.byref(ct), B, _ptr(r), float(discount), float(eps), ms,
+                                        1 if mean else 0, _ptr(val), _ptr(n_iter), _ptr(status), mode, _stream()))
+    last_info = SweepInfo(n_iter, status)
+    return val
+
+
+def svf(tables, p_initial, terminal_mask_t, policy, eps=1e-5, max_sweeps=None, e_features=None,
+        mode=MODE_AUTO):
+    """(4) expected_svf_from_policy, maxent.py:63-114.  policy [S,A] or [B,S,A].
+    With e_features ([S] or [B,S], identity features) also returns grad = e_features - svf."""
+    global last_info
+    torch = require_cuda()
+    S, A = tables.S, tables.A
+    pol = to_device(policy)
+    if pol.dim() == 2:
+        pol = pol.unsqueeze(0)
+    B = int(pol.shape[0])
+    if tuple(pol.shape[1:]) != (S, A):
+        raise EngineError("policy must have shape [S, A] or [B, S, A]")
+    p0, p0shared = _maybe_shared(p_initial, S, B)
+    mask, mshared = _maybe_shared(terminal_mask_t, S, B, torch.uint8)
+    out = torch.empty((B, S), dtype=torch.float64, device=pol.device)
+    grad, ef = None, None
+    if e_features is not None:
+        ef, efshared = _maybe_shared(e_features, S, B)
+        if efshared != p0shared:
+            raise EngineError("e_features and p_initial must both be shared or both per-problem")
+        grad = torch.empty((B, S), dtype=torch.float64, device=pol.device)
+    n_iter = torch.zeros(B, dtype=torch.int32, device=pol.device)
+    status = torch.zeros(B, dtype=torch.int32, device=pol.device)
+    ct = tables.c_struct(_tables_shared(tables, B))
+    ms = DEFAULT_MAX_SWEEPS if max_sweeps is None else int(max_sweeps)
+    _check(_lib.irlb200_svf(ctypes.byref(ct), B, _ptr(p0), p0shared, _ptr(mask), mshared, _ptr(pol), float(eps), ms,
+                            _ptr(out), _ptr(ef), _ptr(grad), _ptr(n_iter), _ptr(status), mode, _stream()))
+    last_info = SweepInfo(n_iter, status)
+    return (out, grad) if grad is not None else out
+
+
+def expected_svf(tables, p_initial, terminal_mask_t, reward, causal=False, phi=None, discount=0.0,
+                 eps_lap=1e-5, eps_svf=1e-5, n_backward=None, max_sweeps=None, e_features=None,
+                 want_policy=False, fused=None):
+    """compute_expected_svf (maxent.py:162-193) / compute_expected_causal_svf (:344-380).
+
+    fused=True: one launch per batch, policy kept in shared memory (lowest latency).
+    fused=False: policy pass and forward pass as two launches with their own
+    occupancy-optimal shapes (highest batch throughput).  None: fused for B < 64.
+    Returns (svf, grad or None, policy or None)."""
+    global last_info
+    torch = require_cuda()
+    S, A = tables.S, tables.A
+    r, B = _batch2d(reward, S)
+    if fused is None:
+        fused = B < 64
+    if fused and (2 + A) * S + 34 > _lib.irlb200_max_states_cta() * 6 + 34:
+        fused = False
+    mask, mshared = _maybe_shared(terminal_mask_t, S, B, torch.uint8)
+    if not fused:
+        if causal:
+            pol = soft_vi(tables, phi, r, discount, eps_lap, max_sweeps)
+        else:
+            pol = backward(tables, mask, r, n_backward)
+        info_a = last_info
+        res = svf(tables, p_initial, mask, pol, eps_svf, max_sweeps, e_features)
+        if causal:
+            last_info = SweepInfo(torch.stack([info_a.n_iter, last_info.n_iter], 1),
+                                  torch.stack([info_a.status, last_info.status], 1))
+        else:
+            nb = torch.full_like(last_info.n_iter, 2 * S if n_backward is None else n_backward)
+            last_info = SweepInfo(torch.stack([nb, last_info.n_iter], 1),
+                                  torch.stack([torch.zeros_like(last_info.status), last_info.status], 1))
+        d, g = res if e_features is not None else (res, None)
+        return d, g, (pol if want_policy else None)
+
+    p0, p0shared = _maybe_shared(p_initial, S, B)
+    ph = None
+    if causal:
+        ph, pshared = _maybe_shared(phi, S, B)
+        if pshared != mshared:
+            raise EngineError("phi and terminal mask must both be shared or both per-problem")
+    out = torch.empty((B, S), dtype=torch.float64, device=r.device)
+    grad, ef = None, None
+    if e_features is not None:
+        ef, efshared = _maybe_shared(e_features, S, B)
+        if efshared != p0shared:
+            raise EngineError("e_features and p_initial must both be shared or both per-problem")
+        grad = torch.empty((B, S), dtype=torch.float64, device=r.device)
+    pol = torch.empty((B, S, A), dtype=torch.float64, device=r.device) if want_policy else None
+    n_iter = torch.zeros((B, 2), dtype=torch.int32, device=r.device)
+    status = torch.zeros((B, 2), dtype=torch.int32, device=r.device)
+    ct = tables.c_struct(_tables_shared(tables, B))
+    ms = DEFAULT_MAX_SWEEPS if max_sweeps is None else int(max_sweeps)
+    _check(_lib.irlb200_expected_svf(
+        ctypes.byref(ct), B, 1 if causal else 0, _ptr(r), _ptr(p0), p0shared, _ptr(mask), _ptr(ph), mshared,
+        2 * S if n_backward is None else int(n_backward), float(discount), float(eps_lap), float(eps_svf), ms,
+        _ptr(out), _ptr(ef), _ptr(grad), _ptr(pol), _ptr(n_iter), _ptr(status), _stream()))
+    last_info = SweepInfo(n_iter, status)
+    return out, grad, pol
+
+
+def features_dot(features, theta):
+    """reward = features . theta (maxent.py:244), dense features [S,F] on the device."""
+    torch = require_cuda()
+    S, F = features.shape
+    out = torch.empty(S, dtype=torch.float64, device=features.device)
+    _check(_lib.irlb200_features_dot(_ptr(features), S, F, _ptr(theta), _ptr(out), _stream()))
+    return out
+
+
+def features_grad(features, svf_t, e_features):
+    """grad = e_features - features^T . svf (maxent.py:248)."""
+    torch = require_cuda()
+    S, F = features.shape
+    out = torch.empty(F, dtype=torch.float64, device=features.device)
+    _check(_lib.irlb200_features_grad(_ptr(features), S, F, _ptr(svf_t), _ptr(e_features), _ptr(out), _stream()))
+    return out

@@ -1,0 +1,21 @@
+// host_util.h -- error reporting and cached device workspaces (host side).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "../../include/irl_maxent_b200.h"
+
+namespace irlb200 {
+
+// record a message for irlb200_last_error() and return `code`
+int fail(int code, const char *msg);
+int fail_cuda(cudaError_t e, const char *what);
+int device_count_impl();
+
+// Cached per-device scratch allocations, grown on demand and reused by later
+// calls (slot 0: predecessor weights of the streamed forward pass, slot 1:
+// iterate buffers + barrier state of the cooperative kernels, slot 2: misc).
+// Calls that use the same slot must be issued on one stream per device.
+int workspace(int slot, size_t bytes, void **out);
+
+}  // namespace irlb200

@@ -1,0 +1,582 @@
+// sweep_kernels.cu -- __global__ wrappers around phases.cuh and their launchers.
+//
+//   *_cta_kernel    grid = B problems, one CTA each (iterate in shared memory)
+//   *_grid_kernel   one problem, cooperative persistent grid (iterate in L2/HBM)
+//   step_cta_kernel fused gradient step: policy phase + forward phase, the
+//                   policy stays in shared memory
+#include <cstdio>
+#include <mutex>
+
+#include "host_util.h"
+#include "phases.cuh"
+
+namespace irlb200 {
+
+// ---------------------------------------------------------------------------
+// batched argument blocks (passed by value as kernel parameters)
+// ---------------------------------------------------------------------------
+struct SuccBatch {
+    SuccArgs a;                  // pointers of problem 0
+    size_t tab_idx_stride;       // elements between the tables of consecutive problems (0: shared)
+    size_t tab_p_stride;
+    size_t phi_stride, term_stride;   // 0: shared
+    int32_t *n_iter, *status;    // [B] or null
+    int out_stride;              // ints between the (n_iter,status) of consecutive problems
+};
+
+struct SvfBatch {
+    SvfArgs a;
+    size_t tab_idx_stride, tab_p_stride;
+    size_t p0_stride, term_stride, ef_stride;
+    int32_t *n_iter, *status;
+    int out_stride;
+};
+
+struct StepBatch {
+    SuccArgs s;
+    SvfArgs f;
+    size_t succ_idx_stride, succ_p_stride, pred_idx_stride, pred_p_stride;
+    size_t phi_stride, term_stride, p0_stride, ef_stride;
+    int32_t *n_iter, *status;    // [B][2]
+    double *policy_out;          // [B][S][A] or null
+};
+
+__device__ __forceinline__ void offset_succ(SuccArgs &a, const SuccBatch &bt, size_t b) {
+    const size_t S = a.S, A = a.A;
+    a.idx += b * bt.tab_idx_stride;
+    a.p += b * bt.tab_p_stride;
+    a.reward += b * S;
+    if (a.phi) a.phi += b * bt.phi_stride;
+    if (a.term) a.term += b * bt.term_stride;
+    if (a.policy) a.policy += b * S * A;
+    if (a.policy2) a.policy2 += b * S * A;
+    if (a.value) a.value += b * S;
+}
+
+__device__ __forceinline__ void offset_svf(SvfArgs &a, const SvfBatch &bt, size_t b) {
+    const size_t S = a.S, A = a.A;
+    a.idx += b * bt.tab_idx_stride;
+    a.p += b * bt.tab_p_stride;
+    a.p0 += b * bt.p0_stride;
+    a.term += b * bt.term_stride;
+    a.policy += b * S * A;
+    if (a.w_scratch) a.w_scratch += b * S * (size_t)a.K;
+    a.svf += b * S;
+    if (a.grad) {
+        a.grad += b * S;
+        a.e_features += b * bt.ef_stride;
+    }
+}
+
+// shared-memory carve-up of the CTA topology: [buf0 | buf1 | scratch(32) | flags | extra...]
+__device__ __forceinline__ double *carve_cta(CtaTopo &tp, int S) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *base = reinterpret_cast<double *>(smem_raw);
+    tp.buf[0] = base;
+    tp.buf[1] = base + S;
+    tp.scratch = base + 2 * (size_t)S;
+    tp.flag = reinterpret_cast<int *>(tp.scratch + 32);
+    tp.vseq = 0;
+    return tp.scratch + 34;      // first free double after the flags
+}
+
+static size_t cta_smem_bytes(int S, int A, bool with_policy) {
+    size_t n = 2 * (size_t)S + 34 + (with_policy ? (size_t)S * A : 0);
+    return n * sizeof(double);
+}
+
+// ---------------------------------------------------------------------------
+// CTA kernels
+// ---------------------------------------------------------------------------
+template <int OP, int A_T, int K_T, int SPT_T, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) succ_cta_kernel(const SuccBatch bt) {
+    CtaTopo tp;
+    SuccArgs a = bt.a;
+    carve_cta(tp, a.S);
+    offset_succ(a, bt, blockIdx.x);
+    int *ni = bt.n_iter ? bt.n_iter + (size_t)blockIdx.x * bt.out_stride : nullptr;
+    int *st = bt.status ? bt.status + (size_t)blockIdx.x * bt.out_stride : nullptr;
+    succ_phase<CtaTopo, OP, A_T, K_T, SPT_T>(tp, a, ni, st);
+}
+
+template <int A_T, int K_T, int SPT_T, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) svf_cta_kernel(const SvfBatch bt) {
+    CtaTopo tp;
+    SvfArgs a = bt.a;
+    carve_cta(tp, a.S);
+    offset_svf(a, bt, blockIdx.x);
+    int *ni = bt.n_iter ? bt.n_iter + (size_t)blockIdx.x * bt.out_stride : nullptr;
+    int *st = bt.status ? bt.status + (size_t)blockIdx.x * bt.out_stride : nullptr;
+    svf_phase<CtaTopo, A_T, K_T, SPT_T>(tp, a, ni, st);
+}
+
+template <bool CAUSAL, int A_T, int K_T, int SPT_T, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) step_cta_kernel(const StepBatch bt) {
+    CtaTopo tp;
+    SuccArgs s = bt.s;
+    SvfArgs f = bt.f;
+    double *pol = carve_cta(tp, s.S);
+    const size_t b = blockIdx.x, S = s.S, A = s.A;
+    s.idx += b * bt.succ_idx_stride;
+    s.p += b * bt.succ_p_stride;
+    s.reward += b * S;
+    if (s.phi) s.phi += b * bt.phi_stride;
+    if (s.term) s.term += b * bt.term_stride;
+    s.policy = pol;
+    s.policy2 = bt.policy_out ? bt.policy_out + b * S * A : nullptr;
+    s.value = nullptr;
+    f.idx += b * bt.pred_idx_stride;
+    f.p += b * bt.pred_p_stride;
+    f.p0 += b * bt.p0_stride;
+    f.term += b * bt.term_stride;
+    f.policy = pol;
+    if (f.w_scratch) f.w_scratch += b * S * (size_t)f.K;
+    f.svf += b * S;
+    if (f.grad) {
+        f.grad += b * S;
+        f.e_features += b * bt.ef_stride;
+    }
+    int *ni = bt.n_iter ? bt.n_iter + 2 * b : nullptr;
+    int *st = bt.status ? bt.status + 2 * b : nullptr;
+    succ_phase<CtaTopo, CAUSAL ? kOpSoftVI : kOpBackward, A_T, K_T, SPT_T>(tp, s, ni, st);
+    svf_phase<CtaTopo, A_T, K_T, SPT_T>(tp, f, ni ? ni + 1 : nullptr, st ? st + 1 : nullptr);
+}
+
+// ---------------------------------------------------------------------------
+// grid (cooperative) kernels -- one problem
+// ---------------------------------------------------------------------------
+struct GridWork {
+    double *buf0, *buf1;
+    GridSyncState *gs;
+};
+
+__device__ __forceinline__ void carve_grid(GridTopo &tp, const GridWork &w) {
+    __shared__ double s_scratch[32];
+    __shared__ unsigned long long s_word;
+    __shared__ int s_flag;
+    tp.buf[0] = w.buf0;
+    tp.buf[1] = w.buf1;
+    tp.gs = w.gs;
+    tp.seq = 0;
+    tp.scratch = s_scratch;
+    tp.s_word = &s_word;
+    tp.flag = &s_flag;
+}
+
+template <int OP, int A_T, int K_T, int SPT_T, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+    succ_grid_kernel(const SuccArgs a, const GridWork w, int32_t *n_iter, int32_t *status) {
+    GridTopo tp;
+    carve_grid(tp, w);
+    succ_phase<GridTopo, OP, A_T, K_T, SPT_T>(tp, a, n_iter, status);
+}
+
+template <int A_T, int K_T, int SPT_T, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+    svf_grid_kernel(const SvfArgs a, const GridWork w, int32_t *n_iter, int32_t *status) {
+    GridTopo tp;
+    carve_grid(tp, w);
+    svf_phase<GridTopo, A_T, K_T, SPT_T>(tp, a, n_iter, status);
+}
+
+// ---------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------
+template <class Kern>
+static int prep_smem(Kern k, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(smem)");
+    }
+    return IRLB200_OK;
+}
+
+static inline int round_up32(int x) { return (x + 31) & ~31; }
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+#define LAUNCH_CHECK(what)                                     \
+    do {                                                       \
+        cudaError_t e__ = cudaGetLastError();                  \
+        if (e__ != cudaSuccess) return fail_cuda(e__, what);   \
+    } while (0)
+
+// fast path = the table shape of every 4-action grid world
+static inline bool is_fast_shape(int A, int K) { return A == 4 && K == 5; }
+
+// ---- CTA: successor phases --------------------------------------------------
+template <int OP>
+static int launch_succ_cta(const SuccBatch &bt, int B, cudaStream_t st) {
+    const int S = bt.a.S, A = bt.a.A, K = bt.a.K;
+    const size_t smem = cta_smem_bytes(S, A, false);
+    const bool fast = is_fast_shape(A, K);
+    const int force_stream = env_int("IRLB200_FORCE_STREAMED", 0);
+    if (fast && S <= 512 && !force_stream) {
+        auto k = succ_cta_kernel<OP, 4, 5, 1, 512, 1>;
+        if (int rc = prep_smem(k, smem)) return rc;
+        k<<<B, round_up32(S), smem, st>>>(bt);
+    } else if (fast && S <= 1024 && !force_stream) {
+        auto k = succ_cta_kernel<OP, 4, 5, 2, 512, 1>;
+        if (int rc = prep_smem(k, smem)) return rc;
+        k<<<B, round_up32((S + 1) / 2), smem, st>>>(bt);
+    } else if (fast) {
+        auto k = succ_cta_kernel<OP, 4, 5, 0, 1024, 1>;
+        if (int rc = prep_smem(k, smem)) return rc;
+        k<<<B, S < 1024 ? round_up32(S) : 1024, smem, st>>>(bt);
+    } else {
+        if (A > kMaxDynA) return fail(IRLB200_EINVAL, "run-time A > 16 is not supported");
+        auto k = succ_cta_kernel<OP, 0, 0, 0, 1024, 1>;
+        if (int rc = prep_smem(k, smem)) return rc;
+        k<<<B, S < 1024 ? round_up32(S) : 1024, smem, st>>>(bt);
+    }
+    LAUNCH_CHECK("succ_cta_kernel");
+    return IRLB200_OK;
+}
+
+// ---- CTA: forward phase -----------------------------------------------------
+static int launch_svf_cta(SvfBatch bt, int B, cudaStream_t st) {
+    const int S = bt.a.S, A = bt.a.A, K = bt.a.K;
+    const size_t smem = cta_smem_bytes(S, A, false);
+    const bool fast = is_fast_shape(A, K);
+    const int force_stream = env_int("IRLB200_FORCE_STREAMED", 0);
+    const int spt_pref = env_int("IRLB200_SVF_SPT", 0);
+    if (fast && !force_stream && S <= 4096) {
+        int spt = spt_pref ? spt_pref : (S <= 256 ? 1 : (S <= 2048 ? 2 : 4));
+        if (spt == 1 && S > 1024) spt = 2;
+        if (spt == 2 && S > 2048) spt = 4;
+        bt.a.w_scratch = nullptr;
+        if (spt == 1) {
+            auto k = svf_cta_kernel<4, 5, 1, 1024, 1>;
+            if (int rc = prep_smem(k, smem)) return rc;
+            k<<<B, round_up32(S), smem, st>>>(bt);
+        } else if (spt == 2) {
+            auto k = svf_cta_kernel<4, 5, 2, 1024, 1>;
+            if (int rc = prep_smem(k, smem)) return rc;
+            k<<<B, round_up32((S + 1) / 2), smem, st>>>(bt);
+        } else {
+            auto k = svf_cta_kernel<4, 5, 4, 1024, 1>;
+            if (int rc = prep_smem(k, smem)) return rc;
+            k<<<B, round_up32((S + 3) / 4), smem, st>>>(bt);
+        }
+    } else {
+        if (A > kMaxDynA) return fail(IRLB200_EINVAL, "run-time A > 16 is not supported");
+        double *ws = nullptr;
+        if (int rc = workspace(0, (size_t)B * S * K * sizeof(double), (void **)&ws)) return rc;
+        bt.a.w_scratch = ws;
+        if (fast) {
+            auto k = svf_cta_kernel<4, 5, 0, 1024, 1>;
+            if (int rc = prep_smem(k, smem)) return rc;
+            k<<<B, S < 1024 ? round_up32(S) : 1024, smem, st>>>(bt);
+        } else {
+            auto k = svf_cta_kernel<0, 0, 0, 1024, 1>;
+            if (int rc = prep_smem(k, smem)) return rc;
+            k<<<B, S < 1024 ? round_up32(S) : 1024, smem, st>>>(bt);
+        }
+    }
+    LAUNCH_CHECK("svf_cta_kernel");
+    return IRLB200_OK;
+}
+
+// ---- CTA: fused step ----------------------------------------------------------
+template <bool CAUSAL>
+static int launch_step_cta(StepBatch bt, int B, cudaStream_t st) {
+    const int S = bt.s.S, A = bt.s.A;
+    const size_t smem = cta_smem_bytes(S, A, true);
+    const bool fast = is_fast_shape(A, bt.s.K) && is_fast_shape(A, bt.f.K);
+    const int force_stream = env_int("IRLB200_FORCE_STREAMED", 0);
+    if (fast && S <= 512 && !force_stream) {
+        bt.f.w_scratch = nullptr;
+        auto k = step_cta_kernel<CAUSAL, 4, 5, 1, 512>;
+        if (int rc = prep_smem(k, smem)) return rc;
+        k<<<B, round_up32(S), smem, st>>>(bt);
+    } else if (fast && S <= 1024 && !force_stream) {
+        bt.f.w_scratch = nullptr;
+        auto k = step_cta_kernel<CAUSAL, 4, 5, 2, 512>;
+        if (int rc = prep_smem(k, smem)) return rc;
+        k<<<B, round_up32((S + 1) / 2), smem, st>>>(bt);
+    } else {
+        if (A > kMaxDynA) return fail(IRLB200_EINVAL, "run-time A > 16 is not supported");
+        if (bt.s.K != bt.f.K && fast) return fail(IRLB200_EINVAL, "internal: fused fast shape mismatch");
+        double *ws = nullptr;
+        if (int rc = workspace(0, (size_t)B * S * bt.f.K * sizeof(double), (void **)&ws)) return rc;
+        bt.f.w_scratch = ws;
+        if (fast) {
+            auto k = step_cta_kernel<CAUSAL, 4, 5, 0, 1024>;
+            if (int rc = prep_smem(k, smem)) return rc;
+            k<<<B, S < 1024 ? round_up32(S) : 1024, smem, st>>>(bt);
+        } else {
+            // run-time shapes: the two phases may have different K; the phase
+            // templates read K from their own argument block when K_T == 0
+            auto k = step_cta_kernel<CAUSAL, 0, 0, 0, 1024>;
+            if (int rc = prep_smem(k, smem)) return rc;
+            k<<<B, S < 1024 ? round_up32(S) : 1024, smem, st>>>(bt);
+        }
+    }
+    LAUNCH_CHECK("step_cta_kernel");
+    return IRLB200_OK;
+}
+
+// ---- grid ---------------------------------------------------------------------
+struct GridPlan {
+    int blocks, threads;
+};
+
+template <class Kern>
+static int plan_grid(Kern k, int S, int threads, int states_per_thread, GridPlan *out) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, 0);
+    if (e != cudaSuccess) return fail_cuda(e, "occupancy");
+    if (per_sm < 1) return fail(IRLB200_ELIMIT, "grid kernel does not fit on an SM");
+    long long want = ((long long)S + (long long)threads * states_per_thread - 1) /
+                     ((long long)threads * states_per_thread);
+    long long cap = (long long)sms * per_sm;
+    int max_blocks = env_int("IRLB200_GRID_BLOCKS", 0);
+    if (max_blocks > 0 && max_blocks < cap) cap = max_blocks;
+    out->blocks = (int)(want < cap ? want : cap);
+    if (out->blocks < 1) out->blocks = 1;
+    out->threads = threads;
+    return IRLB200_OK;
+}
+
+static int grid_work(int S, GridWork *w, cudaStream_t st) {
+    // workspace slot 1: [GridSyncState | buf0 | buf1]
+    const size_t hdr = 256;
+    unsigned char *base = nullptr;
+    if (int rc = workspace(1, hdr + 2 * (size_t)S * sizeof(double), (void **)&base)) return rc;
+    w->gs = reinterpret_cast<GridSyncState *>(base);
+    w->buf0 = reinterpret_cast<double *>(base + hdr);
+    w->buf1 = w->buf0 + S;
+    cudaError_t e = cudaMemsetAsync(base, 0, hdr, st);
+    if (e != cudaSuccess) return fail_cuda(e, "memset(grid sync)");
+    return IRLB200_OK;
+}
+
+template <class Kern, class Args>
+static int launch_coop(Kern k, const GridPlan &pl, const Args &a, const GridWork &w, int32_t *n_iter,
+                       int32_t *status, cudaStream_t st) {
+    void *params[] = {(void *)&a, (void *)&w, (void *)&n_iter, (void *)&status};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)k, dim3(pl.blocks), dim3(pl.threads), params, 0, st);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaLaunchCooperativeKernel");
+    return IRLB200_OK;
+}
+
+template <int OP>
+static int launch_succ_grid(const SuccArgs &a, int32_t *n_iter, int32_t *status, cudaStream_t st) {
+    GridWork w;
+    if (int rc = grid_work(a.S, &w, st)) return rc;
+    GridPlan pl;
+    const bool fast = is_fast_shape(a.A, a.K);
+    const int threads = env_int("IRLB200_GRID_THREADS", 256);
+    if (fast) {
+        // register-resident rows when one state per thread covers the problem
+        auto kr = succ_grid_kernel<OP, 4, 5, 1, 256, 1>;
+        GridPlan pr;
+        if (int rc = plan_grid(kr, a.S, 256, 1, &pr)) return rc;
+        if ((long long)pr.blocks * 256 >= a.S && !env_int("IRLB200_FORCE_STREAMED", 0))
+            return launch_coop(kr, pr, a, w, n_iter, status, st);
+        auto k = succ_grid_kernel<OP, 4, 5, 0, 512, 1>;
+        if (int rc = plan_grid(k, a.S, threads, 1, &pl)) return rc;
+        return launch_coop(k, pl, a, w, n_iter, status, st);
+    }
+    if (a.A > kMaxDynA) return fail(IRLB200_EINVAL, "run-time A > 16 is not supported");
+    auto k = succ_grid_kernel<OP, 0, 0, 0, 512, 1>;
+    if (int rc = plan_grid(k, a.S, threads, 1, &pl)) return rc;
+    return launch_coop(k, pl, a, w, n_iter, status, st);
+}
+
+static int launch_svf_grid(SvfArgs a, int32_t *n_iter, int32_t *status, cudaStream_t st) {
+    GridWork w;
+    if (int rc = grid_work(a.S, &w, st)) return rc;
+    GridPlan pl;
+    const bool fast = is_fast_shape(a.A, a.K);
+    const int threads = env_int("IRLB200_GRID_THREADS", 256);
+    if (fast) {
+        auto kr = svf_grid_kernel<4, 5, 1, 256, 1>;
+        GridPlan pr;
+        if (int rc = plan_grid(kr, a.S, 256, 1, &pr)) return rc;
+        if ((long long)pr.blocks * 256 >= a.S && !env_int("IRLB200_FORCE_STREAMED", 0)) {
+            a.w_scratch = nullptr;
+            return launch_coop(kr, pr, a, w, n_iter, status, st);
+        }
+    }
+    double *ws = nullptr;
+    if (int rc = workspace(0, (size_t)a.S * a.K * sizeof(double), (void **)&ws)) return rc;
+    a.w_scratch = ws;
+    if (fast) {
+        auto k = svf_grid_kernel<4, 5, 0, 512, 1>;
+        if (int rc = plan_grid(k, a.S, threads, 1, &pl)) return rc;
+        return launch_coop(k, pl, a, w, n_iter, status, st);
+    }
+    if (a.A > kMaxDynA) return fail(IRLB200_EINVAL, "run-time A > 16 is not supported");
+    auto k = svf_grid_kernel<0, 0, 0, 512, 1>;
+    if (int rc = plan_grid(k, a.S, threads, 1, &pl)) return rc;
+    return launch_coop(k, pl, a, w, n_iter, status, st);
+}
+
+}  // namespace irlb200
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+using namespace irlb200;
+
+static int max_states_cta_impl() {
+    int dev = 0, optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    // fused step needs (2 + A) * S + 34 doubles; quote the A = 4 figure
+    long long s = ((long long)optin / 8 - 34) / 6;
+    return (int)(s < 0 ? 0 : s);
+}
+
+extern "C" int irlb200_max_states_cta(void) { return max_states_cta_impl(); }
+extern "C" int irlb200_max_states_cluster(void) { return 0; }   // cluster mode: not built yet
+
+static int check_tables(const irlb200_tables *t, bool need_succ, bool need_pred) {
+    if (!t) return fail(IRLB200_EINVAL, "tables == NULL");
+    if (t->S <= 0 || t->A <= 0) return fail(IRLB200_EINVAL, "S and A must be positive");
+    if (need_succ && (!t->succ_idx || !t->succ_p || t->Ks <= 0)) return fail(IRLB200_EINVAL, "successor table missing");
+    if (need_pred && (!t->pred_idx || !t->pred_p || t->Kp <= 0)) return fail(IRLB200_EINVAL, "predecessor table missing");
+    return IRLB200_OK;
+}
+
+static int pick_mode(int mode, int B, int S, int A, bool fused, int *out) {
+    if (device_count_impl() <= 0) return fail(IRLB200_ECUDA, "no CUDA device");
+    int dev = 0, optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const bool fits_cta = cta_smem_bytes(S, A, fused) <= (size_t)optin;
+    if (mode == IRLB200_MODE_AUTO) mode = (fits_cta && (B > 1 || S <= 2048)) ? IRLB200_MODE_CTA : IRLB200_MODE_GRID;
+    if (mode == IRLB200_MODE_CLUSTER) return fail(IRLB200_ELIMIT, "cluster mode is not available in this build");
+    if (mode == IRLB200_MODE_CTA && !fits_cta) return fail(IRLB200_ELIMIT, "problem does not fit one CTA's shared memory");
+    if (mode == IRLB200_MODE_GRID && B != 1) return fail(IRLB200_ELIMIT, "grid mode takes one problem per call");
+    if (mode != IRLB200_MODE_CTA && mode != IRLB200_MODE_GRID) return fail(IRLB200_EINVAL, "unknown mode");
+    *out = mode;
+    return IRLB200_OK;
+}
+
+static void fill_succ(SuccArgs &a, const irlb200_tables *t) {
+    a = SuccArgs{};
+    a.S = t->S; a.A = t->A; a.K = t->Ks;
+    a.idx = t->succ_idx; a.p = t->succ_p;
+}
+
+static void succ_strides(SuccBatch &bt, const irlb200_tables *t) {
+    bt.tab_idx_stride = t->shared ? 0 : (size_t)t->Ks * t->S;
+    bt.tab_p_stride = t->shared ? 0 : (size_t)t->A * t->Ks * t->S;
+}
+
+extern "C" int irlb200_backward(const irlb200_tables *t, int B, const double *reward,
+                                const uint8_t *terminal_mask, int mask_shared, int n_sweeps,
+                                double *policy, int mode, void *stream) {
+    if (int rc = check_tables(t, true, false)) return rc;
+    if (B <= 0 || !reward || !terminal_mask || !policy || n_sweeps < 0) return fail(IRLB200_EINVAL, "backward: bad argument");
+    if (int rc = pick_mode(mode, B, t->S, t->A, false, &mode)) return rc;
+    SuccBatch bt{};
+    fill_succ(bt.a, t);
+    bt.a.reward = reward; bt.a.term = terminal_mask; bt.a.n_sweeps = n_sweeps; bt.a.policy = policy;
+    succ_strides(bt, t);
+    bt.term_stride = mask_shared ? 0 : (size_t)t->S;
+    if (mode == IRLB200_MODE_CTA) return launch_succ_cta<kOpBackward>(bt, B, (cudaStream_t)stream);
+    return launch_succ_grid<kOpBackward>(bt.a, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int irlb200_soft_vi(const irlb200_tables *t, int B, const double *reward,
+                               const double *phi, int phi_shared, double discount, double eps,
+                               int max_sweeps, double *policy, double *value_out,
+                               int32_t *n_iter, int32_t *status, int mode, void *stream) {
+    if (int rc = check_tables(t, true, false)) return rc;
+    if (B <= 0 || !reward || !phi || !policy) return fail(IRLB200_EINVAL, "soft_vi: bad argument");
+    if (int rc = pick_mode(mode, B, t->S, t->A, false, &mode)) return rc;
+    SuccBatch bt{};
+    fill_succ(bt.a, t);
+    bt.a.reward = reward; bt.a.phi = phi; bt.a.discount = discount; bt.a.eps = eps;
+    bt.a.max_sweeps = max_sweeps; bt.a.policy = policy; bt.a.value = value_out;
+    succ_strides(bt, t);
+    bt.phi_stride = phi_shared ? 0 : (size_t)t->S;
+    bt.n_iter = n_iter; bt.status = status; bt.out_stride = 1;
+    if (mode == IRLB200_MODE_CTA) return launch_succ_cta<kOpSoftVI>(bt, B, (cudaStream_t)stream);
+    return launch_succ_grid<kOpSoftVI>(bt.a, n_iter, status, (cudaStream_t)stream);
+}
+
+extern "C" int irlb200_value_iteration(const irlb200_tables *t, int B, const double *reward,
+                                       double discount, double eps, int max_sweeps, int kind,
+                                       double *value, int32_t *n_iter, int32_t *status,
+                                       int mode, void *stream) {
+    if (int rc = check_tables(t, true, false)) return rc;
+    if (B <= 0 || !reward || !value) return fail(IRLB200_EINVAL, "value_iteration: bad argument");
+    if (int rc = pick_mode(mode, B, t->S, t->A, false, &mode)) return rc;
+    SuccBatch bt{};
+    fill_succ(bt.a, t);
+    bt.a.reward = reward; bt.a.discount = discount; bt.a.eps = eps; bt.a.max_sweeps = max_sweeps;
+    bt.a.vi_mean = kind ? 1 : 0; bt.a.value = value;
+    succ_strides(bt, t);
+    bt.n_iter = n_iter; bt.status = status; bt.out_stride = 1;
+    if (mode == IRLB200_MODE_CTA) return launch_succ_cta<kOpVI>(bt, B, (cudaStream_t)stream);
+    return launch_succ_grid<kOpVI>(bt.a, n_iter, status, (cudaStream_t)stream);
+}
+
+static void fill_svf(SvfArgs &a, const irlb200_tables *t) {
+    a = SvfArgs{};
+    a.S = t->S; a.A = t->A; a.K = t->Kp;
+    a.idx = t->pred_idx; a.p = t->pred_p;
+}
+
+extern "C" int irlb200_svf(const irlb200_tables *t, int B, const double *p_initial, int p0_shared,
+                           const uint8_t *terminal_mask, int mask_shared, const double *policy,
+                           double eps, int max_sweeps, double *svf, const double *e_features,
+                           double *grad, int32_t *n_iter, int32_t *status, int mode, void *stream) {
+    if (int rc = check_tables(t, false, true)) return rc;
+    if (B <= 0 || !p_initial || !terminal_mask || !policy || !svf) return fail(IRLB200_EINVAL, "svf: bad argument");
+    if (grad && !e_features) return fail(IRLB200_EINVAL, "svf: grad requested without e_features");
+    if (int rc = pick_mode(mode, B, t->S, t->A, false, &mode)) return rc;
+    SvfBatch bt{};
+    fill_svf(bt.a, t);
+    bt.a.p0 = p_initial; bt.a.term = terminal_mask; bt.a.policy = policy; bt.a.eps = eps;
+    bt.a.max_sweeps = max_sweeps; bt.a.svf = svf; bt.a.e_features = e_features; bt.a.grad = grad;
+    bt.tab_idx_stride = t->shared ? 0 : (size_t)t->Kp * t->S;
+    bt.tab_p_stride = t->shared ? 0 : (size_t)t->A * t->Kp * t->S;
+    bt.p0_stride = p0_shared ? 0 : (size_t)t->S;
+    bt.term_stride = mask_shared ? 0 : (size_t)t->S;
+    bt.ef_stride = p0_shared ? 0 : (size_t)t->S;
+    bt.n_iter = n_iter; bt.status = status; bt.out_stride = 1;
+    if (mode == IRLB200_MODE_CTA) return launch_svf_cta(bt, B, (cudaStream_t)stream);
+    return launch_svf_grid(bt.a, n_iter, status, (cudaStream_t)stream);
+}
+
+extern "C" int irlb200_expected_svf(const irlb200_tables *t, int B, int causal,
+                                    const double *reward, const double *p_initial, int p0_shared,
+                                    const uint8_t *terminal_mask, const double *phi, int mask_shared,
+                                    int n_backward, double discount, double eps_lap, double eps_svf,
+                                    int max_sweeps, double *svf, const double *e_features, double *grad,
+                                    double *policy_out, int32_t *n_iter, int32_t *status, void *stream) {
+    if (int rc = check_tables(t, true, true)) return rc;
+    if (B <= 0 || !reward || !p_initial || !terminal_mask || !svf) return fail(IRLB200_EINVAL, "expected_svf: bad argument");
+    if (causal && !phi) return fail(IRLB200_EINVAL, "expected_svf: causal needs phi");
+    if (grad && !e_features) return fail(IRLB200_EINVAL, "expected_svf: grad requested without e_features");
+    int mode = IRLB200_MODE_CTA;
+    if (int rc = pick_mode(IRLB200_MODE_CTA, B, t->S, t->A, true, &mode)) return rc;
+    StepBatch bt{};
+    fill_succ(bt.s, t);
+    bt.s.reward = reward; bt.s.phi = phi; bt.s.term = terminal_mask; bt.s.discount = discount;
+    bt.s.eps = eps_lap; bt.s.n_sweeps = n_backward; bt.s.max_sweeps = max_sweeps;
+    fill_svf(bt.f, t);
+    bt.f.p0 = p_initial; bt.f.term = terminal_mask; bt.f.eps = eps_svf; bt.f.max_sweeps = max_sweeps;
+    bt.f.svf = svf; bt.f.e_features = e_features; bt.f.grad = grad;
+    bt.succ_idx_stride = t->shared ? 0 : (size_t)t->Ks * t->S;
+    bt.succ_p_stride = t->shared ? 0 : (size_t)t->A * t->Ks * t->S;
+    bt.pred_idx_stride = t->shared ? 0 : (size_t)t->Kp * t->S;
+    bt.pred_p_stride = t->shared ? 0 : (size_t)t->A * t->Kp * t->S;
+    bt.phi_stride = mask_shared ? 0 : (size_t)t->S;
+    bt.term_stride = mask_shared ? 0 : (size_t)t->S;
+    bt.p0_stride = p0_shared ? 0 : (size_t)t->S;
+    bt.ef_stride = p0_shared ? 0 : (size_t)t->S;
+    bt.n_iter = n_iter; bt.status = status; bt.policy_out = policy_out;
+    return causal ? launch_step_cta<true>(bt, B, (cudaStream_t)stream)
+                  : launch_step_cta<false>(bt, B, (cudaStream_t)stream);
+}

@@ -1,0 +1,222 @@
+"""
+maxent -- Maximum-Entropy (Ziebart 2008) and Maximum-Causal-Entropy (Ziebart
+2010) inverse reinforcement learning on B200.
+
+Drop-in for the reference module of the same name (`/root/reference/src/maxent.py`):
+same function names, argument order, keyword names and defaults, same return
+values.  The three fixed-point loops (partition-function sweeps :154-156, soft
+value iteration :326-338, state-visitation sweeps :108-112) run as persistent
+sm_100a kernels behind the C ABI in include/irl_maxent_b200.h; this module only
+moves arguments to the device and back.
+
+Type rule: numpy in -> numpy out, CUDA tensor in -> CUDA tensor out.
+`p_transition` may be the reference's dense `[S, S', A]` table (numpy or CUDA
+tensor; compressed once and cached) or a pre-built `_irlb200.Tables` handle
+(e.g. `gridworld.IcyGridWorld(...).tables()`), which is the only option for
+state counts whose dense table cannot exist.
+
+Differences from the reference, by design:
+  * the non-causal backward pass is range-extended (exact power-of-two
+    rescaling): where the raw loop overflows to NaN (n >= 13 with reward >= 0)
+    this module returns the finite, correctly normalised policy; where the raw
+    loop is finite the results agree to the last few ulp;
+  * every convergence loop has a very large max-sweep guard
+    (`_irlb200.DEFAULT_MAX_SWEEPS`) instead of looping forever;
+  * there is no CPU fallback.
+"""
+
+import numpy as np
+
+import _irlb200 as E
+
+
+# -- helpers -------------------------------------------------------------------
+
+def _wants_tensor(*xs):
+    return any(E.is_tensor(x) for x in xs)
+
+
+def _out(t, as_tensor):
+    return t if as_tensor else t.cpu().numpy()
+
+
+def _is_identity(features):
+    if E.is_tensor(features):
+        return False        # checked on the host only; tensors go through the dense kernels
+    f = np.asarray(features)
+    return f.ndim == 2 and f.shape[0] == f.shape[1] and np.array_equal(f, np.identity(f.shape[0]))
+
+
+# -- common functions (host side, once per irl call) -----------------------------
+
+def feature_expectation_from_trajectories(features, trajectories):
+    """Mean over trajectories of the summed feature rows of every visited state
+    (reference: maxent.py:15-39).  Accumulates in visiting order, so the result is
+    bit-identical with the reference's running sum.  Host side, once per irl call."""
+    f = features.cpu().numpy() if E.is_tensor(features) else np.asarray(features)
+    fe = np.zeros(f.shape[1])
+    n = 0
+    for t in trajectories:
+        for s in t.states():
+            fe += f[s, :]
+        n += 1
+    return fe / n
+
+
+def initial_probabilities_from_trajectories(n_states, trajectories):
+    """Empirical start-state distribution (reference: maxent.py:42-60)."""
+    p = np.zeros(n_states)
+    n = 0
+    for t in trajectories:
+        p[t.transitions()[0][0]] += 1.0
+        n += 1
+    return p / n
+
+
+# -- forward pass ----------------------------------------------------------------
+
+def expected_svf_from_policy(p_transition, p_initial, terminal, p_action, eps=1e-5):
+    """Expected state visitation frequencies of a policy (reference: maxent.py:63-114).
+    `terminal` must be a collection of state indices (as in the reference, :99)."""
+    tables = E.as_tables(p_transition)
+    as_t = _wants_tensor(p_initial, p_action)
+    mask = E.terminal_mask(terminal, tables.S)
+    d = E.svf(tables, p_initial, mask, p_action, eps)
+    return _out(d[0], as_t)
+
+
+# -- plain maximum entropy ---------------------------------------------------------
+
+def local_action_probabilities(p_transition, terminal, reward):
+    """Backward pass of MaxEnt IRL, 2*S partition sweeps (reference: maxent.py:119-159)."""
+    tables = E.as_tables(p_transition)
+    mask = E.terminal_mask(terminal, tables.S)
+    pol = E.backward(tables, mask, reward)
+    return _out(pol[0], _wants_tensor(reward))
+
+
+def compute_expected_svf(p_transition, p_initial, terminal, reward, eps=1e-5):
+    """Backward pass + forward pass in one launch (reference: maxent.py:162-193)."""
+    tables = E.as_tables(p_transition)
+    mask = E.terminal_mask(terminal, tables.S)
+    d, _, _ = E.expected_svf(tables, p_initial, mask, reward, causal=False, eps_svf=eps)
+    return _out(d[0], _wants_tensor(p_initial, reward))
+
+
+# -- maximum causal entropy ----------------------------------------------------------
+
+def softmax(x1, x2):
+    """Soft maximum max + log(1 + exp(min - max)) (reference: maxent.py:260-276).
+    Elementwise helper kept for API compatibility; the kernels fold it on chip."""
+    if _wants_tensor(x1, x2):
+        torch = E._torch()
+        x1, x2 = torch.as_tensor(x1), torch.as_tensor(x2)
+        hi, lo = torch.maximum(x1, x2), torch.minimum(x1, x2)
+        return hi + torch.log(1.0 + torch.exp(lo - hi))
+    hi, lo = np.maximum(x1, x2), np.minimum(x1, x2)
+    return hi + np.log(1.0 + np.exp(lo - hi))
+
+
+def local_causal_action_probabilities(p_transition, terminal, reward, discount, eps=1e-5):
+    """Soft value iteration + causal policy (reference: maxent.py:279-341).
+    `terminal`: index collection, or the terminal reward function iff len == S."""
+    tables = E.as_tables(p_transition)
+    phi = E.terminal_phi(terminal, tables.S)
+    pol = E.soft_vi(tables, phi, reward, discount, eps)
+    return _out(pol[0], _wants_tensor(reward))
+
+
+def compute_expected_causal_svf(p_transition, p_initial, terminal, reward, discount,
+                                eps_lap=1e-5, eps_svf=1e-5):
+    """Soft-VI + forward pass in one launch (reference: maxent.py:344-380)."""
+    tables = E.as_tables(p_transition)
+    mask = E.terminal_mask(terminal, tables.S)
+    phi = E.terminal_phi(terminal, tables.S)
+    d, _, _ = E.expected_svf(tables, p_initial, mask, reward, causal=True, phi=phi, discount=discount,
+                             eps_lap=eps_lap, eps_svf=eps_svf)
+    return _out(d[0], _wants_tensor(p_initial, reward))
+
+
+# -- outer gradient loops ------------------------------------------------------------
+
+def _irl_loop(p_transition, features, terminal, trajectories, optim, init, eps, step):
+    """Shared body of irl / irl_causal (reference: maxent.py:229-255, :426-453).
+
+    omega (`theta`) lives on the device for the whole optimisation; the optimizer
+    steps it in place through the reference it was handed in `reset` (the
+    reference relies on exactly this aliasing, :236-252).  The host blocks once
+    per gradient step, on the scalar `delta`.
+    """
+    torch = E.require_cuda()
+    tables = E.as_tables(p_transition)
+    S = tables.S
+    as_t = _wants_tensor(features)
+    identity = _is_identity(features)
+    n_features = features.shape[1]
+
+    e_features = feature_expectation_from_trajectories(features, trajectories)
+    p_initial = initial_probabilities_from_trajectories(S, trajectories)
+    e_features_d, p_initial_d = E.to_device(e_features), E.to_device(p_initial)
+    features_d = None if identity else E.to_device(features)
+    mask = E.terminal_mask(terminal, S)
+
+    theta = E.to_device(init(n_features))
+    optim.reset(theta)
+    delta = np.inf
+    while delta > eps:
+        theta_old = theta.clone()
+        # identity features: features.dot(theta) is theta itself, bit for bit
+        reward = theta if identity else E.features_dot(features_d, theta)
+        e_svf, grad = step(tables, p_initial_d, mask, reward, e_features_d if identity else None)
+        if not identity:
+            grad = E.features_grad(features_d, e_svf[0], e_features_d)
+        else:
+            grad = grad[0]
+        optim.step(grad)
+        delta = torch.max(torch.abs(theta_old - theta)).item()      # the one host sync per step
+
+    reward = theta.clone() if identity else E.features_dot(features_d, theta)
+    return _out(reward, as_t)
+
+
+def irl(p_transition, features, terminal, trajectories, optim, init, eps=1e-4, eps_esvf=1e-5):
+    """Maximum-entropy IRL; returns the per-state reward `features . theta`
+    (reference: maxent.py:196-255)."""
+    def step(tables, p0, mask, reward, ef):
+        d, g, _ = E.expected_svf(tables, p0, mask, reward, causal=False, eps_svf=eps_esvf, e_features=ef)
+        return d, g
+    return _irl_loop(p_transition, features, terminal, trajectories, optim, init, eps, step)
+
+
+def irl_causal(p_transition, features, terminal, trajectories, optim, init, discount,
+               eps=1e-4, eps_svf=1e-5, eps_lap=1e-5):
+    """Maximum-causal-entropy IRL; returns the per-state reward
+    (reference: maxent.py:383-453)."""
+    S = E.as_tables(p_transition).S
+    phi = E.terminal_phi(terminal, S)
+    # the forward pass needs an index list (reference: maxent.py:99); an array-valued
+    # `terminal` is only meaningful for the policy pass, exactly as in the reference
+
+    def step(tables, p0, mask, reward, ef):
+        d, g, _ = E.expected_svf(tables, p0, mask, reward, causal=True, phi=phi, discount=discount,
+                                 eps_lap=eps_lap, eps_svf=eps_svf, e_features=ef)
+        return d, g
+    return _irl_loop(p_transition, features, terminal, trajectories, optim, init, eps, step)
+
+
+# -- batched mode (no counterpart in the reference: B independent problems) ------------
+
+def compute_expected_svf_batch(tables, p_initial, terminal, reward, eps=1e-5, causal=False,
+                               discount=None, eps_lap=1e-5, e_features=None, fused=None):
+    """B independent gradient-step bodies in one or two launches.
+
+    tables: `Tables` with 1 (shared) or B worlds; reward [B,S]; p_initial [S] or [B,S];
+    terminal: index collection shared by all problems.  Returns (svf [B,S], grad or None).
+    """
+    S = tables.S
+    mask = E.terminal_mask(terminal, S)
+    phi = E.terminal_phi(terminal, S) if causal else None
+    d, g, _ = E.expected_svf(tables, p_initial, mask, reward, causal=causal, phi=phi,
+                             discount=discount if causal else 0.0, eps_lap=eps_lap, eps_svf=eps,
+                             e_features=e_features, fused=fused)
+    return d, g

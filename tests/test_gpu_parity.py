@@ -1,0 +1,457 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the
+reference-generated golden fixtures.  Needs a B200: `pytest -m gpu`.
+
+Tolerance (BASELINE.json north_star): float64 mode within 1e-10 relative on SVF,
+policy and learned reward, identical iteration counts.  Indices and table values
+are compared bit-exactly.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import _irlb200 as E
+import gridworld as W
+import maxent as M
+import optimizer as O
+import solver as S
+import trajectory as T
+
+from oracle import dense_port as D
+from oracle import sparse_port as SP
+from test_oracle_golden import load_trajectories
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+def close(a, b, rtol=RTOL, atol=1e-300):
+    a = a.cpu().numpy() if E.is_tensor(a) else np.asarray(a)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+def counts():
+    return E.last_info.counts()
+
+
+@pytest.fixture(params=["auto", "streamed", "grid", "grid_streamed"])
+def variant(request, monkeypatch):
+    """Run the same parity checks through every execution variant of the kernels."""
+    v = request.param
+    if "streamed" in v:
+        monkeypatch.setenv("IRLB200_FORCE_STREAMED", "1")
+    return E.MODE_GRID if v.startswith("grid") else E.MODE_AUTO
+
+
+# ------------------------------------------------------------------ tables ---
+
+def expected_tables(P):
+    """Reference structure straight from the dense table with numpy."""
+    S, _, A = P.shape
+    nz = (P != 0).any(axis=2)
+    succ = [np.nonzero(nz[s])[0] for s in range(S)]
+    pred = [np.nonzero(nz[:, s])[0] for s in range(S)]
+    return succ, pred
+
+
+def check_tables(t, P):
+    S, _, A = P.shape
+    succ, pred = expected_tables(P)
+    si, sp = t.succ_idx[0].cpu().numpy(), t.succ_p[0].cpu().numpy()
+    pi, pp = t.pred_idx[0].cpu().numpy(), t.pred_p[0].cpu().numpy()
+    assert si.shape == (t.Ks, S) and sp.shape == (A, t.Ks, S)
+    for s in range(S):
+        n = len(succ[s])
+        assert np.array_equal(si[:n, s], succ[s]), "successor indices must be bit-exact"
+        assert (si[n:, s] == s).all() and (sp[:, n:, s] == 0).all()
+        assert np.array_equal(sp[:, :n, s], P[s, succ[s], :].T)
+        m = len(pred[s])
+        assert np.array_equal(pi[:m, s], pred[s]), "predecessor indices must be bit-exact"
+        assert (pi[m:, s] == s).all() and (pp[:, m:, s] == 0).all()
+        assert np.array_equal(pp[:, :m, s], P[pred[s], s, :].T)
+
+
+@pytest.mark.parametrize("key", ["icy_1_0.2", "icy_2_0.2", "icy_3_0.35", "icy_5_0.2", "icy_8_0.2", "grid_5", "grid_2"])
+def test_compress_dense_worlds(golden, key):
+    P = golden("worlds")[key]
+    t = E.compress_dense(P)
+    check_tables(t, P)
+    succ, pred = expected_tables(P)
+    assert t.k_discovered == (max(map(len, succ)), max(map(len, pred)))
+
+
+@pytest.mark.parametrize("i", range(6))
+def test_compress_dense_random(golden, i):
+    P = golden("random_mdps")["r%d_P" % i]
+    check_tables(E.compress_dense(P), P)
+
+
+@pytest.mark.parametrize("n,p,icy", [(1, 0.2, True), (2, 0.2, True), (5, 0.2, True), (8, 0.35, True),
+                                     (5, 0.0, False), (17, 0.1, True)])
+def test_direct_world_tables_equal_compressed_dense(golden, n, p, icy):
+    """gridworld_tables (no dense detour) == compress(dense), bit for bit; and the
+    device-built dense table == the reference's table."""
+    Pd = E.gridworld_dense(n, p, icy)
+    key = ("icy_%d_%s" % (n, p)) if icy else "grid_%d" % n
+    g = golden("worlds")
+    if key in g.files:
+        assert np.array_equal(Pd.cpu().numpy(), g[key])
+    else:
+        ref = D.icy_gridworld_table(n, p) if icy else D.gridworld_table(n)
+        assert np.array_equal(Pd.cpu().numpy(), ref)
+    a = E.compress_dense(Pd)
+    b = E.gridworld_tables(n, p, icy=icy)
+    if a.Ks == 5 and a.Kp == 5:
+        for x, y in ((a.succ_idx, b.succ_idx), (a.succ_p, b.succ_p), (a.pred_idx, b.pred_idx), (a.pred_p, b.pred_p)):
+            assert (x == y).all()
+    check_tables(b, Pd.cpu().numpy())
+
+
+def test_batched_world_tables():
+    ps = [0.1, 0.2, 0.3]
+    t = E.gridworld_tables(6, ps)
+    assert t.n_tables == 3
+    for b, p in enumerate(ps):
+        check_tables(t.select(b), D.icy_gridworld_table(6, p))
+
+
+# ------------------------------------------------------- per-kernel parity ---
+
+def test_backward_5x5(golden, variant):
+    g, P = golden("kernels"), golden("worlds")["icy_5_0.2"]
+    t = E.compress_dense(P)
+    pol = E.backward(t, E.terminal_mask([24], 25), g["k5_reward"], mode=variant)
+    close(pol[0], g["k5_lap"])
+    pol = E.backward(t, E.terminal_mask([24, 4], 25), g["k5b_reward"], mode=variant)
+    close(pol[0], g["k5b_lap"])
+
+
+def test_svf_5x5(golden, variant):
+    g, P = golden("kernels"), golden("worlds")["icy_5_0.2"]
+    t = E.compress_dense(P)
+    d = E.svf(t, g["k5_p0"], E.terminal_mask([24], 25), g["k5_lap"], 1e-5, mode=variant)
+    assert counts()[0] == int(g["k5_svf_n"]) == 72
+    close(d[0], g["k5_svf"])
+    d = E.svf(t, g["k5b_p0"], E.terminal_mask([24, 4], 25), g["k5b_lap"], 1e-7, mode=variant)
+    assert counts()[0] == int(g["k5b_svf_n"])
+    close(d[0], g["k5b_svf"])
+
+
+@pytest.mark.parametrize("gamma", [0.7, 0.9])
+def test_soft_vi_5x5(golden, variant, gamma):
+    g, P = golden("kernels"), golden("worlds")["icy_5_0.2"]
+    t = E.compress_dense(P)
+    pol = E.soft_vi(t, E.terminal_phi([24], 25), g["k5_reward"], gamma, 1e-5, mode=variant)
+    assert counts()[0] == int(g["k5_lcap_%s_n" % gamma])
+    close(pol[0], g["k5_lcap_%s" % gamma])
+    d = E.svf(t, g["k5_p0"], E.terminal_mask([24], 25), pol[0], 1e-5, mode=variant)
+    assert counts()[0] == int(g["k5_csvf_%s_n" % gamma])
+    close(d[0], g["k5_csvf_%s" % gamma])
+
+
+def test_soft_vi_terminal_reward_array(golden, variant):
+    g, P = golden("kernels"), golden("worlds")["icy_5_0.2"]
+    t = E.compress_dense(P)
+    pol = E.soft_vi(t, E.terminal_phi(g["k5_phi"], 25), g["k5_reward"], 0.8, 1e-6, mode=variant)
+    assert counts()[0] == int(g["k5_lcap_phi_n"])
+    close(pol[0], g["k5_lcap_phi"])
+
+
+def test_value_iteration_5x5(golden, variant):
+    g, P = golden("kernels"), golden("worlds")["icy_5_0.2"]
+    t = E.compress_dense(P)
+    v = E.value_iteration(t, g["k5_reward"], 0.7, 1e-3, mode=variant)
+    assert counts()[0] == 21
+    close(v[0], g["k5_vi"])
+    v = E.value_iteration(t, g["k5_reward"], 0.9, 1e-6, mode=variant)
+    assert counts()[0] == int(g["k5_vi9_n"])
+    close(v[0], g["k5_vi9"])
+
+
+@pytest.mark.parametrize("n", [8, 12])
+def test_larger_grids(golden, variant, n):
+    g = golden("kernels")
+    S, pre = n * n, "k%d_" % n
+    t = E.gridworld_tables(n, 0.2)
+    p0 = np.zeros(S); p0[0] = 1.0
+    mask, phi = E.terminal_mask([S - 1], S), E.terminal_phi([S - 1], S)
+    pol = E.backward(t, mask, g[pre + "reward"], mode=variant)
+    close(pol[0], g[pre + "lap"])
+    d = E.svf(t, p0, mask, g[pre + "lap"], mode=variant)
+    assert counts()[0] == int(g[pre + "svf_n"])
+    close(d[0], g[pre + "svf"])
+    pol = E.soft_vi(t, phi, g[pre + "greward"], 0.9, mode=variant)
+    assert counts()[0] == int(g[pre + "lcap_n"])
+    close(pol[0], g[pre + "lcap"])
+    d = E.svf(t, p0, mask, g[pre + "lcap"], mode=variant)
+    assert counts()[0] == int(g[pre + "csvf_n"])
+    close(d[0], g[pre + "csvf"])
+    v = E.value_iteration(t, g[pre + "greward"], 0.95, 1e-5, mode=variant)
+    assert counts()[0] == int(g[pre + "vi_n"])
+    close(v[0], g[pre + "vi"])
+
+
+@pytest.mark.parametrize("i", range(6))
+def test_random_mdps(golden, variant, i):
+    """Non-grid MDPs: run-time A and K, ragged rows."""
+    g, pre = golden("random_mdps"), "r%d_" % i
+    P = g[pre + "P"]
+    S = P.shape[0]
+    term = list(g[pre + "terminal"])
+    t = E.compress_dense(P)
+    mask, phi = E.terminal_mask(term, S), E.terminal_phi(term, S)
+    close(E.backward(t, mask, g[pre + "reward"], mode=variant)[0], g[pre + "lap"])
+    pol = E.soft_vi(t, phi, g[pre + "reward"], 0.85, mode=variant)
+    assert counts()[0] == int(g[pre + "lcap_n"])
+    close(pol[0], g[pre + "lcap"])
+    d = E.svf(t, g[pre + "p0"], mask, g[pre + "pol"], mode=variant)
+    assert counts()[0] == int(g[pre + "svf_n"])
+    close(d[0], g[pre + "svf"])
+    v = E.value_iteration(t, g[pre + "reward"], 0.9, 1e-6, mode=variant)
+    assert counts()[0] == int(g[pre + "vi_n"])
+    close(v[0], g[pre + "vi"])
+
+
+def test_overflow_regime_is_range_extended(golden):
+    """13x13, reward == 1: the raw reference returns NaN; the product equals the
+    range-extended oracle (SURVEY TL;DR 2)."""
+    P = D.icy_gridworld_table(13, 0.2)
+    ext = D.local_action_probabilities(P, [168], np.ones(169), rescale=True)
+    pol = M.local_action_probabilities(P, [168], np.ones(169))
+    assert np.isfinite(pol).all()
+    close(pol, ext)
+    # underflow side
+    ext = D.local_action_probabilities(P, [168], np.full(169, -6.0), rescale=True)
+    close(M.local_action_probabilities(P, [168], np.full(169, -6.0)), ext)
+
+
+def test_guards_and_status(golden):
+    g, P = golden("kernels"), golden("worlds")["icy_5_0.2"]
+    t = E.compress_dense(P)
+    E.svf(t, g["k5_p0"], E.terminal_mask([24], 25), g["k5_lap"], 1e-5, max_sweeps=10)
+    assert counts()[0] == 10 and E.last_info.stati()[0] == E.ST_MAXSWEEPS
+    # NaN ends the loop in the sweep it appears (reference: `while delta > eps`)
+    pol = np.array(g["k5_lap"]); pol[3, 1] = np.nan
+    E.svf(t, g["k5_p0"], E.terminal_mask([24], 25), pol, 1e-5)
+    assert E.last_info.stati()[0] == E.ST_NONFINITE
+    d_ref, n_ref = D.expected_svf_from_policy(P, g["k5_p0"], [24], pol)
+    assert counts()[0] <= n_ref + 8     # dense 0*NaN poisons at once, sparse needs a few hops
+
+
+# ------------------------------------------------------------- public API ---
+
+def test_module_api_numpy_roundtrip(golden):
+    g, P = golden("kernels"), golden("worlds")["icy_5_0.2"]
+    pa = M.local_action_probabilities(P, [24], g["k5_reward"])
+    assert isinstance(pa, np.ndarray) and pa.shape == (25, 4)
+    close(pa, g["k5_lap"])
+    close(M.expected_svf_from_policy(P, g["k5_p0"], [24], pa), g["k5_svf"])
+    close(M.compute_expected_svf(P, g["k5_p0"], [24], g["k5_reward"]), g["k5_svf"])
+    close(M.local_causal_action_probabilities(P, [24], g["k5_reward"], 0.9), g["k5_lcap_0.9"])
+    close(M.compute_expected_causal_svf(P, g["k5_p0"], [24], g["k5_reward"], 0.7), g["k5_csvf_0.7"])
+    v = S.value_iteration(P, g["k5_reward"], 0.7)
+    assert isinstance(v, np.ndarray) and v.shape == (25,)
+    close(v, g["k5_vi"])
+    close(M.softmax(np.array([1.0, -np.inf]), np.array([2.0, 3.0])), D.softmax(np.array([1.0, -np.inf]), np.array([2.0, 3.0])))
+
+
+def test_module_api_tensor_in_tensor_out(golden):
+    import torch
+    g, P = golden("kernels"), golden("worlds")["icy_5_0.2"]
+    Pt = torch.as_tensor(P).cuda()
+    r = torch.as_tensor(g["k5_reward"]).cuda()
+    pa = M.local_action_probabilities(Pt, [24], r)
+    assert isinstance(pa, torch.Tensor) and pa.is_cuda
+    close(pa, g["k5_lap"])
+    d = M.compute_expected_svf(W.IcyGridWorld(5).tables(), torch.as_tensor(g["k5_p0"]).cuda(), [24], r)
+    assert d.is_cuda
+    close(d, g["k5_svf"])
+    v = S.value_iteration(Pt, r, 0.7)
+    assert v.is_cuda
+    close(v, g["k5_vi"])
+
+
+def test_fused_step_matches_split(golden):
+    g = golden("kernels")
+    t = E.gridworld_tables(8, 0.2)
+    p0 = np.zeros(64); p0[0] = 1.0
+    mask, phi = E.terminal_mask([63], 64), E.terminal_phi([63], 64)
+    for fused in (True, False):
+        d, grad, pol = E.expected_svf(t, p0, mask, g["k8_reward"], causal=False, e_features=p0,
+                                      want_policy=True, fused=fused)
+        close(d[0], g["k8_svf"])
+        close(pol[0], g["k8_lap"])
+        close(grad[0], p0 - g["k8_svf"], atol=1e-12)
+        assert E.last_info.counts()[0, 1] == int(g["k8_svf_n"])
+        d, _, pol = E.expected_svf(t, p0, mask, g["k8_greward"], causal=True, phi=phi, discount=0.9,
+                                   want_policy=True, fused=fused)
+        close(d[0], g["k8_csvf"])
+        close(pol[0], g["k8_lcap"])
+        assert tuple(E.last_info.counts()[0]) == (int(g["k8_lcap_n"]), int(g["k8_csvf_n"]))
+
+
+def test_expert_pipeline_and_solver_helpers(golden):
+    g, k = golden("e2e_5x5"), golden("kernels")
+    world = W.IcyGridWorld(5, 0.2)
+    value = S.value_iteration(world.p_transition, k["k5_reward"], 0.7)
+    close(value, g["expert_value"])
+    pol = S.stochastic_policy_from_value(world, g["expert_value"], w=lambda x: x ** 5)
+    assert np.array_equal(pol, g["expert_policy"])
+    greedy = S.optimal_policy(world, k["k5_reward"], 0.7)
+    ref = np.array([np.argmax([g["expert_value"][world.state_index_transition(s, a)] for a in range(4)])
+                    for s in range(25)])
+    assert np.array_equal(greedy, ref)
+    sv = S.stochastic_value_iteration(world.p_transition, k["k5_reward"], 0.7)
+    assert sv.shape == (25,) and np.isfinite(sv).all()
+
+
+# ------------------------------------------------------------- end to end ---
+
+class _Count:
+    def __init__(self, inner):
+        self.inner, self.n = inner, 0
+
+    def reset(self, p):
+        self.inner.reset(p)
+
+    def step(self, g, *a, **k):
+        self.n += 1
+        return self.inner.step(g, *a, **k)
+
+
+def test_irl_5x5_like_main(golden):
+    """The call sequence of the reference's main.py (main.py:54-72) on the fixture
+    trajectories: 375 outer steps, learned reward to 1e-10."""
+    g = golden("e2e_5x5")
+    world = W.IcyGridWorld(size=5, p_slip=0.2)
+    tjs = load_trajectories(g)
+    opt = _Count(O.ExpSga(lr=O.linear_decay(lr0=0.2)))
+    r = M.irl(world.p_transition, W.state_features(world), [24], tjs, opt, O.Constant(1.0))
+    assert isinstance(r, np.ndarray)
+    assert opt.n == int(g["irl_steps"]) == 375
+    close(r, g["irl_reward"])
+
+
+@pytest.mark.parametrize("gamma", [0.7, 0.9])
+def test_irl_causal_5x5_like_main(golden, gamma):
+    g = golden("e2e_5x5")
+    world = W.IcyGridWorld(size=5, p_slip=0.2)
+    tjs = load_trajectories(g)
+    opt = _Count(O.ExpSga(lr=O.linear_decay(lr0=0.2)))
+    r = M.irl_causal(world.p_transition, W.state_features(world), [24], tjs, opt, O.Constant(1.0), gamma)
+    assert opt.n == int(g["irl_causal_%s_steps" % gamma])
+    close(r, g["irl_causal_%s_reward" % gamma])
+
+
+def test_irl_other_optimizers_and_dense_features(golden):
+    g = golden("e2e_5x5")
+    world = W.IcyGridWorld(size=5, p_slip=0.2)
+    tjs = load_trajectories(g)
+    feats = W.coordinate_features(world)
+    opt = _Count(O.ExpSga(lr=O.linear_decay(lr0=0.1)))
+    r = M.irl(world.p_transition, feats, [24], tjs, opt, O.Constant(0.2), eps=1e-3)
+    assert opt.n == int(g["irl_expsga_coord_steps"])
+    close(r, g["irl_expsga_coord_reward"])
+    features = W.state_features(world)
+    opt = _Count(O.ExpSga(lr=O.power_decay(lr0=0.3)).normalize_grad())
+    r = M.irl_causal(world.p_transition, features, [24], tjs, opt, O.Constant(1.0), 0.8, eps=1e-3)
+    assert opt.n == int(g["irl_causal_ng_steps"])
+    close(r, g["irl_causal_ng_reward"])
+    opt = _Count(O.Sga(lr=O.exponential_decay(lr0=0.1, decay_rate=0.05)).normalize_grad())
+    r = M.irl_causal(world.p_transition, features, [24], tjs, opt, O.Constant(0.2), 0.8, eps=1e-3)
+    assert opt.n == int(g["irl_causal_sga_steps"])
+    close(r, g["irl_causal_sga_reward"])
+
+
+# -------------------------------------------------- batched + larger sizes ---
+
+def test_batch_equals_loop():
+    """B independent worlds in one launch == B single launches (bitwise)."""
+    n, B = 12, 7
+    S = n * n
+    ps = 0.1 + 0.2 * np.arange(B) / B
+    tabs = E.gridworld_tables(n, ps)
+    rng = np.random.default_rng(5)
+    rewards = -np.log(4.0) + 0.1 * rng.standard_normal((B, S))
+    p0 = np.zeros(S); p0[0] = 1.0
+    for causal in (False, True):
+        for fused in (True, False):
+            d, _ = M.compute_expected_svf_batch(tabs, p0, [S - 1], rewards, causal=causal, discount=0.9, fused=fused)
+            nb = E.last_info.counts()
+            for b in range(B):
+                d1, _ = M.compute_expected_svf_batch(tabs.select(b), p0, [S - 1], rewards[b], causal=causal,
+                                                     discount=0.9, fused=True)
+                assert (d[b] == d1[0]).all()
+                assert (nb[b] == E.last_info.counts()[0]).all()
+    # one of them against the oracle
+    mdp = SP.icy_gridworld_sparse(n, ps[3])
+    pa, n_lap = SP.local_causal_action_probabilities(mdp, [S - 1], rewards[3], 0.9)
+    dref, n_svf = SP.expected_svf_from_policy(mdp, p0, [S - 1], pa)
+    close(d[3], dref)
+    assert tuple(nb[3]) == (n_lap, n_svf)
+
+
+def test_shared_table_batch():
+    n, B = 8, 5
+    S = n * n
+    tabs = E.gridworld_tables(n, 0.2)
+    rng = np.random.default_rng(11)
+    rewards = -np.log(4.0) + 0.1 * rng.standard_normal((B, S))
+    p0 = np.zeros(S); p0[0] = 1.0
+    d, _ = M.compute_expected_svf_batch(tabs, p0, [S - 1], rewards)
+    P = D.icy_gridworld_table(n, 0.2)
+    for b in (0, 4):
+        ref, _ = D.compute_expected_svf(P, p0, [S - 1], rewards[b])
+        close(d[b], ref)
+
+
+def test_32x32_against_sparse_oracle(variant):
+    """C4-sized world (1 024 states), goal-directed reward, causal path."""
+    n = 32
+    S = n * n
+    mdp = SP.icy_gridworld_sparse(n, 0.2)
+    r = np.full(S, -0.1); r[S - 1] = 1.0
+    p0 = np.zeros(S); p0[0] = 1.0
+    pa, n_lap = SP.local_causal_action_probabilities(mdp, [S - 1], r, 0.9)
+    dref, n_svf = SP.expected_svf_from_policy(mdp, p0, [S - 1], pa)
+    t = E.gridworld_tables(n, 0.2)
+    mask, phi = E.terminal_mask([S - 1], S), E.terminal_phi([S - 1], S)
+    pol = E.soft_vi(t, phi, r, 0.9, mode=variant)
+    assert counts()[0] == n_lap
+    close(pol[0], pa)
+    d = E.svf(t, p0, mask, pol[0], mode=variant)
+    assert counts()[0] == n_svf
+    close(d[0], dref)
+    rr = -np.log(4.0) + 0.01 * np.random.default_rng(0).standard_normal(S)
+    pb = SP.local_action_probabilities(mdp, [S - 1], rr)
+    close(E.backward(t, mask, rr, mode=variant)[0], pb)
+
+
+def test_grid_mode_64x64_properties():
+    """Size-independent properties at a size the dense reference cannot reach quickly:
+    policy rows sum to 1; SVF satisfies its own fixed-point equation to eps;
+    sum of visit counts is finite and >= 1."""
+    n = 64
+    S = n * n
+    t = E.gridworld_tables(n, 0.2)
+    r = np.full(S, -0.1); r[S - 1] = 1.0
+    p0 = np.zeros(S); p0[0] = 1.0
+    mask, phi = E.terminal_mask([S - 1], S), E.terminal_phi([S - 1], S)
+    pol = E.soft_vi(t, phi, r, 0.9, mode=E.MODE_GRID)
+    n_grid = counts()[0]
+    pol_c = E.soft_vi(t, phi, r, 0.9, mode=E.MODE_CTA)
+    assert counts()[0] == n_grid
+    assert (pol == pol_c).all(), "grid and CTA variants must agree bitwise"
+    rows = pol[0].sum(dim=1).cpu().numpy()
+    np.testing.assert_allclose(np.delete(rows, S - 1), 1.0, rtol=1e-9)
+    d = E.svf(t, p0, mask, pol[0], mode=E.MODE_GRID)
+    n_grid = counts()[0]
+    d_c = E.svf(t, p0, mask, pol[0], mode=E.MODE_CTA)
+    assert counts()[0] == n_grid and (d == d_c).all()
+    mdp = SP.icy_gridworld_sparse(n, 0.2)
+    keep = np.ones(S); keep[S - 1] = 0
+    dn, poln = d[0].cpu().numpy(), pol[0].cpu().numpy()
+    nxt = p0 + sum(mdp.transposed()[a].dot(keep * poln[:, a] * dn) for a in range(4))
+    assert np.max(np.abs(nxt - dn)) <= 1e-5
+    assert 1.0 <= dn.sum() < 1e6

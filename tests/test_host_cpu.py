@@ -1,0 +1,188 @@
+"""Host-side logic of the product modules, CPU only: world tables, optimizers
+(numpy and torch-CPU tensors), trajectory statistics, C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gridworld as W
+import optimizer as O
+import trajectory as T
+import _irlb200 as E
+
+from test_oracle_golden import load_trajectories
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ worlds ---
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 8])
+def test_world_tables_match_reference(golden, n):
+    g = golden("worlds")
+    assert np.array_equal(W.GridWorld(n).p_transition, g["grid_%d" % n])
+    for p in (0.2, 0.35):
+        assert np.array_equal(W.IcyGridWorld(n, p_slip=p).p_transition, g["icy_%d_%s" % (n, p)])
+
+
+def test_zero_structure_like_reference_test():
+    """Same property the reference's only test checks (src/test_gridworld.py:11-54)."""
+    for world in (W.GridWorld(5), W.IcyGridWorld(5)):
+        n = world.size
+        for f in range(world.n_states):
+            for t in range(world.n_states):
+                if abs(f % n - t % n) + abs(f // n - t // n) > 1:
+                    assert (world.p_transition[f, t, :] == 0.0).all()
+
+
+def test_world_helpers():
+    w = W.IcyGridWorld(5)
+    assert w.n_states == 25 and w.n_actions == 4 and w.actions == [(1, 0), (-1, 0), (0, 1), (0, -1)]
+    assert w.state_index_to_point(7) == (2, 1) and w.state_point_to_index((2, 1)) == 7
+    assert w.state_point_to_index_clipped((-1, 9)) == 20
+    nxt = w.intended_next_states()
+    for s in range(25):
+        for a in range(4):
+            assert nxt[s, a] == w.state_index_transition(s, a)
+    assert np.array_equal(W.state_features(w), np.identity(25))
+    cf = W.coordinate_features(w)
+    assert cf.shape == (25, 5) and cf[7, 2] == 1 and cf[7, 1] == 1 and cf[6, 1] == 2
+    assert repr(w) == "IcyGridWorld(size=5, p_slip=0.2)" and repr(W.GridWorld(3)) == "GridWorld(size=3)"
+
+
+def test_large_world_is_lazy():
+    w = W.IcyGridWorld(128)
+    assert w._dense is None and w.n_states == 16384
+
+
+# --------------------------------------------------------------- optimizers ---
+
+def _run(opt, init, grads, as_torch):
+    th = init(grads.shape[1])
+    if as_torch:
+        import torch
+        th = torch.as_tensor(th)
+        grads = torch.as_tensor(grads)
+    opt.reset(th)
+    for g in grads:
+        opt.step(g)
+    return th.numpy() if as_torch else th
+
+
+@pytest.mark.parametrize("as_torch", [False, True])
+def test_optimizers_match_reference(golden, as_torch):
+    g = golden("optimizer")
+    grads = g["grads"]
+    tol = dict(rtol=1e-14, atol=0) if as_torch else dict(rtol=0, atol=0)
+    cases = {
+        "sga": (O.Sga(lr=0.1), O.Constant(0.5)),
+        "sga_lin": (O.Sga(lr=O.linear_decay(0.2)), O.Constant(0.5)),
+        "expsga": (O.ExpSga(lr=O.linear_decay(0.2)), O.Constant(1.0)),
+        "expsga_norm": (O.ExpSga(lr=0.1, normalize=True), O.Constant(1.0)),
+        "ng_l2": (O.Sga(lr=0.1).normalize_grad(), O.Constant(0.0)),
+        "ng_l1": (O.ExpSga(lr=O.exponential_decay(0.2)).normalize_grad(1), O.Constant(1.0)),
+    }
+    for name, (opt, init) in cases.items():
+        np.testing.assert_allclose(_run(opt, init, grads, as_torch), g[name], err_msg=name, **tol)
+
+
+def test_schedules_and_initializers(golden):
+    g = golden("optimizer")
+    ks = np.arange(12)
+    assert np.array_equal([O.linear_decay(0.2, 0.5, 3)(k) for k in ks], g["linear"])
+    assert np.array_equal([O.power_decay(0.2, 0.5, 2, 3)(k) for k in ks], g["power"])
+    assert np.array_equal([O.exponential_decay(0.2, 0.3, 2)(k) for k in ks], g["expo"])
+    assert np.array_equal(O.Constant(lambda shape: 1.0 / shape)(4), g["const_fn"])
+    np.random.seed(3)
+    a = O.Uniform(0.1, 0.4)(6)
+    np.random.seed(3)
+    assert np.array_equal(a, np.random.uniform(size=6, low=0.1, high=0.4))
+
+
+def test_optimizer_aliasing():
+    """reset() must keep a reference, step() must update in place."""
+    th = np.ones(3)
+    opt = O.ExpSga(lr=0.5).normalize_grad()
+    opt.reset(th)
+    assert opt.parameters is th and opt.opt.parameters is th
+    opt.step(np.array([1.0, 0.0, -1.0]))
+    assert th[0] > 1.0 > th[2]
+
+
+# ------------------------------------------------------------- trajectories ---
+
+def test_trajectory_container():
+    t = T.Trajectory([(0, 1, 5), (5, 2, 6)])
+    assert list(t.states()) == [0, 5, 6] and t.transitions()[0][0] == 0
+    assert repr(t) == "Trajectory([(0, 1, 5), (5, 2, 6)])"
+
+
+def test_trajectory_generation_matches_reference_stream(golden):
+    """Seeded generation consumes numpy's global RNG exactly like the reference (main.py:32-51)."""
+    g = golden("e2e_5x5")
+    world = W.IcyGridWorld(5, 0.2)
+    np.random.seed(0)
+    initial = np.zeros(25); initial[0] = 1.0
+    tjs = list(T.generate_trajectories(200, world, T.stochastic_policy_adapter(g["expert_policy"]), initial, [24]))
+    ref = load_trajectories(g)
+    assert [t.transitions() for t in tjs] == [t.transitions() for t in ref]
+
+
+def test_trajectory_statistics(golden):
+    import maxent as M
+    g = golden("e2e_5x5")
+    tjs = load_trajectories(g)
+    assert np.array_equal(M.feature_expectation_from_trajectories(np.identity(25), tjs), g["e_features"])
+    assert np.array_equal(M.initial_probabilities_from_trajectories(25, tjs), g["p_initial"])
+
+
+# ------------------------------------------------------------------- C ABI ---
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "irl_maxent_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(irlb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert set(_declared_symbols()) == set(E.SIGNATURES)
+
+
+def test_library_loads_and_exports_every_symbol():
+    """dlopen only -- no compute call (there is no GPU in the CPU test tier)."""
+    if not os.path.exists(E.LIB_PATH):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("build_native", os.path.join(ROOT, "irl-maxent_b200", "build_native.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build()
+    lib = ctypes.CDLL(E.LIB_PATH)
+    for name in _declared_symbols():
+        assert hasattr(lib, name), name
+    E.load_library()
+    assert E._lib.irlb200_version() >= 100
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, not compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import maxent as M
+    P = W.IcyGridWorld(3).p_transition
+    with pytest.raises(E.EngineError):
+        M.local_action_probabilities(P, [8], np.zeros(9))
+    with pytest.raises(E.EngineError):
+        E.gridworld_tables(4, 0.2)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "irl-maxent_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.lower(), \
+                    "%s mentions the oracle" % os.path.join(dirpath, f)
