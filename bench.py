@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""
+bench.py -- IRL grad-steps/sec of the MaxEnt gradient-step body on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (one process per GPU under torchrun for N > 1)
+    python bench.py --impl reference --steps K --warmup W    (the reference's CPU arithmetic, host cores)
+
+Workload (BASELINE.json configs[3], SURVEY section 8d "C4"): per GPU a batch of
+B = 4096 independent 32x32 IcyGridWorlds (S = 1024 states, A = 4,
+p_slip_b = 0.1 + 0.2 b / B), identity features, terminal = [S-1], start state 0.
+One step = one gradient-step body of `maxent.irl` (maxent.py:240-252) for every
+world of the batch: reward = omega -> backward pass (2 S partition sweeps) ->
+forward state-visitation pass to eps = 1e-5 -> grad = e_features - svf ->
+Sga step on the device-resident omega.  Rewards start at -ln 4 + 0.01 N(0,1), the
+regime in which the reference's raw backward pass is finite (SURVEY TL;DR 2), so
+the CPU arm computes the same thing.  Scaling is weak: every rank owns its own
+4096 worlds, no collective on the data path; value = all ranks' grad-steps / max
+over ranks of the device time.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "irl-maxent_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "irl_grad_steps_per_sec"
+UNIT = "grad-steps/s"
+SVF_BYTES_PER_STATE_SWEEP = 84      # 20 + 8 w, w = 8: SURVEY section 8(d), merged predecessor weights, Kp = 5
+BWD_BYTES_PER_STATE_SWEEP = 216     # 64 + 19 w
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="worlds per GPU")
+    ap.add_argument("--size", type=int, default=32, help="grid side length")
+    ap.add_argument("--lr", type=float, default=1e-5)
+    ap.add_argument("--max-sweeps", type=int, default=2000000,
+                    help="guard per fixed point (the reference has none); worlds that hit it are reported")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=240.0, help="seconds for the whole reference arm")
+    return ap.parse_args()
+
+
+def workload(args, rank):
+    """Synthetic inputs of one rank (host arrays)."""
+    B, n = args.batch, args.size
+    S = n * n
+    gb = rank * B + np.arange(B)                       # global world ids: weak scaling, distinct worlds per rank
+    p_slip = 0.1 + 0.2 * (gb % 4096) / 4096.0
+    rng = np.random.default_rng(1000 + rank)
+    theta0 = -np.log(4.0) + 0.01 * rng.standard_normal((B, S))
+    r_true = -np.log(4.0) + 0.01 * np.random.default_rng(2000 + rank).standard_normal((B, S))
+    p0 = np.zeros(S)
+    p0[0] = 1.0
+    return dict(B=B, n=n, S=S, p_slip=p_slip, theta0=theta0, r_true=r_true, p0=p0, terminal=[S - 1])
+
+
+def config_dict(args, n_gpus):
+    return {"workload": "C4: batched independent %dx%d IcyGridWorlds, MaxEnt gradient-step body "
+                        "(2S backward sweeps + SVF to eps 1e-5 + Sga step)" % (args.size, args.size),
+            "worlds_per_gpu": args.batch, "states": args.size ** 2, "actions": 4,
+            "eps_svf": 1e-5, "optimizer": "Sga(lr=%g)" % args.lr, "features": "identity",
+            "parallelism": "batch-sharded x%d, no data-path collective" % n_gpus,
+            "l2": "inputs larger than L2: %.2f GB of tables + 0.1 GB of vectors streamed per step"
+                  % (args.batch * args.size ** 2 * 360 / 1e9)}
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        time.sleep(0.05)
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the reference's dense numpy arithmetic (oracle/dense_port.py)
+# ---------------------------------------------------------------------------
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_full_body(w, b):
+    """One complete gradient-step body of world b with the dense port (kind: "port").
+    Table construction is excluded (the reference builds it once, gridworld.py:52)."""
+    from oracle import dense_port as D
+    P = D.icy_gridworld_table(w["n"], w["p_slip"][b])
+    ef = np.zeros(w["S"])
+    t0 = time.perf_counter()
+    d, n_svf = D.compute_expected_svf(P, w["p0"], w["terminal"], w["theta0"][b], 1e-5)
+    grad = ef - d
+    _ = w["theta0"][b] + 1e-3 * grad
+    dt = time.perf_counter() - t0
+    return dt, n_svf
+
+
+def cpu_sampled_body(w, b, n_bw=64, n_fw=256):
+    """Bounded sample of the same body: the per-call dense slicing / copy of the reference
+    (maxent.py:98-102,143) timed in full, n_bw backward and n_fw forward sweeps timed, then
+    scaled to 2S backward sweeps and to the exact forward sweep count of this world (taken
+    from the sparse restatement, not timed)."""
+    from oracle import dense_port as D
+    from oracle import sparse_port as SP
+    S, A = w["S"], 4
+    P = D.icy_gridworld_table(w["n"], w["p_slip"][b])
+    r = w["theta0"][b]
+    t0 = time.perf_counter()
+    er = np.exp(r)
+    per_action = [np.array(P[:, :, a]) for a in range(A)]              # maxent.py:143
+    zs = np.zeros(S)
+    zs[w["terminal"]] = 1.0
+    t_setup_b = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for _ in range(n_bw):
+        za = np.array([er * per_action[a].dot(zs) for a in range(A)]).T    # :155
+        zs = za.sum(axis=1)                                                # :156
+    t_bw = (time.perf_counter() - t0) / n_bw
+    t0 = time.perf_counter()
+    pt = np.copy(P)                                                    # :98
+    pt[w["terminal"], :, :] = 0.0
+    per_action_t = [np.array(pt[:, :, a]) for a in range(A)]           # :102
+    t_setup_f = time.perf_counter() - t0
+    pol = np.full((S, A), 0.25)
+    d = np.zeros(S)
+    t0 = time.perf_counter()
+    for _ in range(n_fw):
+        parts = [per_action_t[a].T.dot(pol[:, a] * d) for a in range(A)]   # :109
+        d_new = w["p0"] + np.array(parts).sum(axis=0)                      # :110
+        _delta, d = np.max(np.abs(d_new - d)), d_new                       # :112
+    t_fw = (time.perf_counter() - t0) / n_fw
+    mdp = SP.icy_gridworld_sparse(w["n"], w["p_slip"][b])
+    pa = SP.local_action_probabilities(mdp, w["terminal"], r)
+    _, n_svf = SP.expected_svf_from_policy(mdp, w["p0"], w["terminal"], pa, 1e-5)
+    total = t_setup_b + t_setup_f + 2 * S * t_bw + n_svf * t_fw
+    return total, n_svf, dict(setup_s=t_setup_b + t_setup_f, backward_ms_per_sweep=1e3 * t_bw,
+                              forward_ms_per_sweep=1e3 * t_fw)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    w = workload(args, 0)
+    cores = blas_threads()
+    total_steps = args.steps + args.warmup
+    full = total_steps * 40.0 <= args.cpu_budget and args.size <= 32
+    times, detail = [], None
+    for i in range(total_steps):
+        b = (i * 409) % w["B"]
+        if full:
+            dt, n_svf = cpu_full_body(w, b)
+        else:
+            dt, n_svf, detail = cpu_sampled_body(w, b)
+        if i >= args.warmup:
+            times.append(dt)
+    mean = float(np.mean(times))
+    value = 1.0 / mean
+    sample = ("one world of the batch per step, " +
+              ("full gradient-step body (2S dense backward sweeps + dense SVF sweeps to eps)" if full else
+               "per-call dense slicing timed in full + 64 backward + 256 forward dense sweeps timed, scaled to "
+               "2S backward sweeps and the world's exact forward sweep count (extrapolated)"))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * mean, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "detail": detail},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------
+
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    import _irlb200 as E
+    import maxent as M
+    import optimizer as O
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    w = workload(args, rank)
+    B, S = w["B"], w["S"]
+    tabs = E.gridworld_tables(w["n"], w["p_slip"])          # setup, outside the timed region
+    p0 = E.to_device(w["p0"])
+    # synthetic expert statistics: the visitation frequencies of a hidden reward
+    e_features, _ = M.compute_expected_svf_batch(tabs, p0, w["terminal"], w["r_true"], fused=False,
+                                                 max_sweeps=args.max_sweeps)
+    theta = E.to_device(w["theta0"])
+    optim = O.Sga(lr=args.lr)
+    optim.reset(theta)
+
+    def step_device():
+        # reward = features . omega with identity features is omega itself (maxent.py:244)
+        svf, grad = M.compute_expected_svf_batch(tabs, p0, w["terminal"], theta, e_features=e_features, fused=False,
+                                                 max_sweeps=args.max_sweeps)
+        optim.step(grad)                                    # maxent.py:251, in place on the device omega
+        return svf, grad
+
+    # ---- device-resident timing ---------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    E.launch_log = []
+    l0 = E.n_launches
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sweeps, stati = [], []
+    t0.record()
+    for _ in range(args.steps):
+        step_device()
+        sweeps.append(E.last_info.n_iter)                   # device tensors, read after the region
+        stati.append(E.last_info.status)
+    t1.record()
+    barrier()
+    launches = E.n_launches - l0
+    log, E.launch_log = E.launch_log, None
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * B * args.steps / (ms_total / 1e3)
+
+    # per-kernel durations (CUDA events on the launching stream) and algorithmic bytes
+    dur = {}
+    for name, a, b in log:
+        dur.setdefault(name, []).append(a.elapsed_time(b))
+    n_fw = np.array([s[:, 1].sum().item() for s in sweeps], dtype=np.float64)      # forward sweeps per launch
+    svf_ms = float(np.mean(dur.get("svf", [float("nan")])))
+    bwd_ms = float(np.mean(dur.get("backward", [float("nan")])))
+    svf_bytes = float(n_fw.mean()) * S * SVF_BYTES_PER_STATE_SWEEP
+    bwd_bytes = float(B) * 2 * S * S * BWD_BYTES_PER_STATE_SWEEP
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = svf_bytes / (svf_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "svf_cta_kernel (forward state-visitation sweeps)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
+                "traffic": None,
+                "algorithmic_bytes_per_launch": svf_bytes, "launch_ms": svf_ms,
+                "share_of_step": svf_ms * args.steps / ms_total if ms_total else None,
+                "forward_sweeps_per_world_mean": float(n_fw.mean()) / B,
+                "forward_sweeps_per_world_max": int(max(int(s[:, 1].max().item()) for s in sweeps)),
+                "worlds_stopped_by_guard": int(sum(int((s[:, 1] == 2).sum().item()) for s in stati)),
+                "note": "tables and weights are register-resident for the whole fixed point, so the algorithmic "
+                        "bytes of a sweep never reach HBM: frac is an efficiency figure against the HBM roofline a "
+                        "streaming implementation would be bound by, not physical DRAM traffic (see DESIGN.md)",
+                "backward": {"launch_ms": bwd_ms, "algorithmic_bytes_per_launch": bwd_bytes,
+                             "achieved": bwd_bytes / (bwd_ms / 1e3) / 1e9 if bwd_ms == bwd_ms else None}}
+
+    # ---- end to end through the public API with host buffers --------------------
+    theta_h = torch.empty((B, S), dtype=torch.float64).pin_memory()
+    theta_h.copy_(torch.as_tensor(w["theta0"]))
+    grad_h = torch.empty((B, S), dtype=torch.float64).pin_memory()
+    ef_dev = e_features
+
+    def step_e2e():
+        th = theta_h.to(dev, non_blocking=True)                             # H2D: this step's omega
+        _, grad = M.compute_expected_svf_batch(tabs, p0, w["terminal"], th, e_features=ef_dev, fused=False,
+                                               max_sweeps=args.max_sweeps)
+        grad_h.copy_(grad, non_blocking=False)                              # D2H: the gradient
+        theta_h.add_(grad_h, alpha=args.lr)                                 # host-side Sga step (optimizer.py:107)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - tw0
+    e2e_ms = torch.tensor([max(e0.elapsed_time(e1), 1e3 * wall)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(e2e_ms.item()) / 1e3)
+
+    line = None
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config_dict(args, world), "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * S * 8,
+                        "d2h_bytes_per_step": B * S * 8},
+                "gpu_launches": int(launches), "roofline": roofline}
+        if world == 1 and not args.no_cpu_baseline:
+            t, n_svf = cpu_full_body(w, 0)
+            line["cpu_baseline"] = {"value": 1.0 / t, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+                                    "sample": "world 0 of the batch, one full gradient-step body with the dense "
+                                              "numpy restatement (2S = %d backward + %d forward dense sweeps), "
+                                              "%.1f s" % (2 * S, n_svf, t)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse()
+    sys.exit(run_reference_arm(a) if a.impl == "reference" else run_b200_arm(a))

@@ -154,12 +154,13 @@ int irlb200_value_iteration(const irlb200_tables *t, int B, const double *reward
  *     W[j][s'] = sum_a P[s_j,s',a] * policy[s_j,a] are formed on chip.
  *   p_initial [B or 1][S], policy [B][S][A], svf [B][S] out
  *   grad      [B][S] out or NULL: fused epilogue for identity features,
- *             grad = e_features - svf   (maxent.py:248 with features = I)
+ *             grad = e_features - svf   (maxent.py:248 with features = I);
+ *             e_features [B or 1][S] (ef_shared = 1: one vector for the whole batch)
  * ------------------------------------------------------------------------- */
 int irlb200_svf(const irlb200_tables *t, int B, const double *p_initial, int p0_shared,
                 const uint8_t *terminal_mask, int mask_shared, const double *policy,
                 double eps, int max_sweeps,
-                double *svf, const double *e_features, double *grad,
+                double *svf, const double *e_features, int ef_shared, double *grad,
                 int32_t *n_iter, int32_t *status, int mode, void *stream);
 
 /* ------------------------------------------------------------------------- *
@@ -173,8 +174,8 @@ int irlb200_expected_svf(const irlb200_tables *t, int B, int causal,
                          const double *reward, const double *p_initial, int p0_shared,
                          const uint8_t *terminal_mask, const double *phi, int mask_shared,
                          int n_backward, double discount, double eps_lap, double eps_svf,
-                         int max_sweeps, double *svf, const double *e_features, double *grad,
-                         double *policy_out /* [B][S][A] or NULL */,
+                         int max_sweeps, double *svf, const double *e_features, int ef_shared,
+                         double *grad, double *policy_out /* [B][S][A] or NULL */,
                          int32_t *n_iter, int32_t *status, void *stream);
 
 /* ------------------------------------------------------------------------- *

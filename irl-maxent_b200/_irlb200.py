@@ -56,9 +56,9 @@ SIGNATURES = {
     "irlb200_backward": ([_tp, _i, _vp, _vp, _i, _i, _vp, _i, _vp], _i),
     "irlb200_soft_vi": ([_tp, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _i, _vp], _i),
     "irlb200_value_iteration": ([_tp, _i, _vp, _d, _d, _i, _i, _vp, _vp, _vp, _i, _vp], _i),
-    "irlb200_svf": ([_tp, _i, _vp, _i, _vp, _i, _vp, _d, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),
+    "irlb200_svf": ([_tp, _i, _vp, _i, _vp, _i, _vp, _d, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp], _i),
     "irlb200_expected_svf": ([_tp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _d, _d, _d, _i,
-                              _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+                              _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "irlb200_features_dot": ([_vp, _i, _i, _vp, _vp, _vp], _i),
     "irlb200_features_grad": ([_vp, _i, _i, _vp, _vp, _vp, _vp], _i),
 }
@@ -328,6 +328,32 @@ class SweepInfo:
 
 last_info = None
 
+# optional per-launch timing: when `launch_log` is a list, every sweep entry point
+# appends (name, start_event, end_event), recorded on the launching stream
+launch_log = None
+n_launches = 0          # launches of this library's kernels since import (bench.py: gpu_launches)
+
+
+class _timed:
+    def __init__(self, name, launches=1):
+        self.name, self.launches = name, launches
+
+    def __enter__(self):
+        global n_launches
+        n_launches += self.launches
+        if launch_log is not None:
+            torch = _torch()
+            self.t0 = torch.cuda.Event(enable_timing=True)
+            self.t1 = torch.cuda.Event(enable_timing=True)
+            self.t0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if launch_log is not None:
+            self.t1.record()
+            launch_log.append((self.name, self.t0, self.t1))
+        return False
+
 
 # ---------------------------------------------------------------------------
 # entry-point wrappers (device tensors in, device tensors out)
@@ -341,8 +367,9 @@ def backward(tables, terminal_mask_t, reward, n_sweeps=None, mode=MODE_AUTO):
     mask, mshared = _maybe_shared(terminal_mask_t, S, B, torch.uint8)
     pol = torch.empty((B, S, A), dtype=torch.float64, device=r.device)
     ct = tables.c_struct(_tables_shared(tables, B))
-    _check(_lib.irlb200_backward(ctypes.byref(ct), B, _ptr(r), _ptr(mask), mshared,
-                                 2 * S if n_sweeps is None else int(n_sweeps), _ptr(pol), mode, _stream()))
+    with _timed("backward"):
+        _check(_lib.irlb200_backward(ctypes.byref(ct), B, _ptr(r), _ptr(mask), mshared,
+                                     2 * S if n_sweeps is None else int(n_sweeps), _ptr(pol), mode, _stream()))
     return pol
 
 
@@ -359,8 +386,9 @@ def soft_vi(tables, phi, reward, discount, eps=1e-5, max_sweeps=None, mode=MODE_
     status = torch.zeros(B, dtype=torch.int32, device=r.device)
     ct = tables.c_struct(_tables_shared(tables, B))
     ms = DEFAULT_MAX_SWEEPS if max_sweeps is None else int(max_sweeps)
-    _check(_lib.irlb200_soft_vi(ctypes.byref(ct), B, _ptr(r), _ptr(ph), pshared, float(discount), float(eps),
-                                ms, _ptr(pol), _ptr(val), _ptr(n_iter), _ptr(status), mode, _stream()))
+    with _timed("soft_vi"):
+        _check(_lib.irlb200_soft_vi(ctypes.byref(ct), B, _ptr(r), _ptr(ph), pshared, float(discount), float(eps),
+                                    ms, _ptr(pol), _ptr(val), _ptr(n_iter), _ptr(status), mode, _stream()))
     last_info = SweepInfo(n_iter, status)
     return (pol, val) if want_value else pol
 
@@ -376,8 +404,9 @@ def value_iteration(tables, reward, discount, eps=1e-3, max_sweeps=None, mean=Fa
     status = torch.zeros(B, dtype=torch.int32, device=r.device)
     ct = tables.c_struct(_tables_shared(tables, B))
     ms = DEFAULT_MAX_SWEEPS if max_sweeps is None else int(max_sweeps)
-    _check(_lib.irlb200_value_iteration(ctypes.byref(ct), B, _ptr(r), float(discount), float(eps), ms,
-                                        1 if mean else 0, _ptr(val), _ptr(n_iter), _ptr(status), mode, _stream()))
+    with _timed("value_iteration"):
+        _check(_lib.irlb200_value_iteration(ctypes.byref(ct), B, _ptr(r), float(discount), float(eps), ms,
+                                            1 if mean else 0, _ptr(val), _ptr(n_iter), _ptr(status), mode, _stream()))
     last_info = SweepInfo(n_iter, status)
     return val
 
@@ -398,18 +427,18 @@ def svf(tables, p_initial, terminal_mask_t, policy, eps=1e-5, max_sweeps=None, e
     p0, p0shared = _maybe_shared(p_initial, S, B)
     mask, mshared = _maybe_shared(terminal_mask_t, S, B, torch.uint8)
     out = torch.empty((B, S), dtype=torch.float64, device=pol.device)
-    grad, ef = None, None
+    grad, ef, efshared = None, None, 1
     if e_features is not None:
         ef, efshared = _maybe_shared(e_features, S, B)
-        if efshared != p0shared:
-            raise EngineError("e_features and p_initial must both be shared or both per-problem")
         grad = torch.empty((B, S), dtype=torch.float64, device=pol.device)
     n_iter = torch.zeros(B, dtype=torch.int32, device=pol.device)
     status = torch.zeros(B, dtype=torch.int32, device=pol.device)
     ct = tables.c_struct(_tables_shared(tables, B))
     ms = DEFAULT_MAX_SWEEPS if max_sweeps is None else int(max_sweeps)
-    _check(_lib.irlb200_svf(ctypes.byref(ct), B, _ptr(p0), p0shared, _ptr(mask), mshared, _ptr(pol), float(eps), ms,
-                            _ptr(out), _ptr(ef), _ptr(grad), _ptr(n_iter), _ptr(status), mode, _stream()))
+    with _timed("svf"):
+        _check(_lib.irlb200_svf(ctypes.byref(ct), B, _ptr(p0), p0shared, _ptr(mask), mshared, _ptr(pol), float(eps), ms,
+                                _ptr(out), _ptr(ef), efshared, _ptr(grad), _ptr(n_iter), _ptr(status), mode,
+                                _stream()))
     last_info = SweepInfo(n_iter, status)
     return (out, grad) if grad is not None else out
 
@@ -456,21 +485,20 @@ def expected_svf(tables, p_initial, terminal_mask_t, reward, causal=False, phi=N
         if pshared != mshared:
             raise EngineError("phi and terminal mask must both be shared or both per-problem")
     out = torch.empty((B, S), dtype=torch.float64, device=r.device)
-    grad, ef = None, None
+    grad, ef, efshared = None, None, 1
     if e_features is not None:
         ef, efshared = _maybe_shared(e_features, S, B)
-        if efshared != p0shared:
-            raise EngineError("e_features and p_initial must both be shared or both per-problem")
         grad = torch.empty((B, S), dtype=torch.float64, device=r.device)
     pol = torch.empty((B, S, A), dtype=torch.float64, device=r.device) if want_policy else None
     n_iter = torch.zeros((B, 2), dtype=torch.int32, device=r.device)
     status = torch.zeros((B, 2), dtype=torch.int32, device=r.device)
     ct = tables.c_struct(_tables_shared(tables, B))
     ms = DEFAULT_MAX_SWEEPS if max_sweeps is None else int(max_sweeps)
-    _check(_lib.irlb200_expected_svf(
-        ctypes.byref(ct), B, 1 if causal else 0, _ptr(r), _ptr(p0), p0shared, _ptr(mask), _ptr(ph), mshared,
-        2 * S if n_backward is None else int(n_backward), float(discount), float(eps_lap), float(eps_svf), ms,
-        _ptr(out), _ptr(ef), _ptr(grad), _ptr(pol), _ptr(n_iter), _ptr(status), _stream()))
+    with _timed("expected_svf_fused"):
+        _check(_lib.irlb200_expected_svf(
+            ctypes.byref(ct), B, 1 if causal else 0, _ptr(r), _ptr(p0), p0shared, _ptr(mask), _ptr(ph), mshared,
+            2 * S if n_backward is None else int(n_backward), float(discount), float(eps_lap), float(eps_svf), ms,
+            _ptr(out), _ptr(ef), efshared, _ptr(grad), _ptr(pol), _ptr(n_iter), _ptr(status), _stream()))
     last_info = SweepInfo(n_iter, status)
     return out, grad, pol
 

@@ -72,8 +72,8 @@ __device__ __forceinline__ void offset_svf(SvfArgs &a, const SvfBatch &bt, size_
 __device__ __forceinline__ double *carve_cta(CtaTopo &tp, int S) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *base = reinterpret_cast<double *>(smem_raw);
-    tp.buf[0] = base;
-    tp.buf[1] = base + S;
+    tp.buf0 = base;
+    tp.buf1 = base + S;
     tp.scratch = base + 2 * (size_t)S;
     tp.flag = reinterpret_cast<int *>(tp.scratch + 32);
     tp.vseq = 0;
@@ -154,8 +154,8 @@ __device__ __forceinline__ void carve_grid(GridTopo &tp, const GridWork &w) {
     __shared__ double s_scratch[32];
     __shared__ unsigned long long s_word;
     __shared__ int s_flag;
-    tp.buf[0] = w.buf0;
-    tp.buf[1] = w.buf1;
+    tp.buf0 = w.buf0;
+    tp.buf1 = w.buf1;
     tp.gs = w.gs;
     tp.seq = 0;
     tp.scratch = s_scratch;
@@ -530,7 +530,8 @@ static void fill_svf(SvfArgs &a, const irlb200_tables *t) {
 extern "C" int irlb200_svf(const irlb200_tables *t, int B, const double *p_initial, int p0_shared,
                            const uint8_t *terminal_mask, int mask_shared, const double *policy,
                            double eps, int max_sweeps, double *svf, const double *e_features,
-                           double *grad, int32_t *n_iter, int32_t *status, int mode, void *stream) {
+                           int ef_shared, double *grad, int32_t *n_iter, int32_t *status, int mode,
+                           void *stream) {
     if (int rc = check_tables(t, false, true)) return rc;
     if (B <= 0 || !p_initial || !terminal_mask || !policy || !svf) return fail(IRLB200_EINVAL, "svf: bad argument");
     if (grad && !e_features) return fail(IRLB200_EINVAL, "svf: grad requested without e_features");
@@ -543,7 +544,7 @@ extern "C" int irlb200_svf(const irlb200_tables *t, int B, const double *p_initi
     bt.tab_p_stride = t->shared ? 0 : (size_t)t->A * t->Kp * t->S;
     bt.p0_stride = p0_shared ? 0 : (size_t)t->S;
     bt.term_stride = mask_shared ? 0 : (size_t)t->S;
-    bt.ef_stride = p0_shared ? 0 : (size_t)t->S;
+    bt.ef_stride = ef_shared ? 0 : (size_t)t->S;
     bt.n_iter = n_iter; bt.status = status; bt.out_stride = 1;
     if (mode == IRLB200_MODE_CTA) return launch_svf_cta(bt, B, (cudaStream_t)stream);
     return launch_svf_grid(bt.a, n_iter, status, (cudaStream_t)stream);
@@ -553,8 +554,9 @@ extern "C" int irlb200_expected_svf(const irlb200_tables *t, int B, int causal,
                                     const double *reward, const double *p_initial, int p0_shared,
                                     const uint8_t *terminal_mask, const double *phi, int mask_shared,
                                     int n_backward, double discount, double eps_lap, double eps_svf,
-                                    int max_sweeps, double *svf, const double *e_features, double *grad,
-                                    double *policy_out, int32_t *n_iter, int32_t *status, void *stream) {
+                                    int max_sweeps, double *svf, const double *e_features, int ef_shared,
+                                    double *grad, double *policy_out, int32_t *n_iter, int32_t *status,
+                                    void *stream) {
     if (int rc = check_tables(t, true, true)) return rc;
     if (B <= 0 || !reward || !p_initial || !terminal_mask || !svf) return fail(IRLB200_EINVAL, "expected_svf: bad argument");
     if (causal && !phi) return fail(IRLB200_EINVAL, "expected_svf: causal needs phi");
@@ -575,7 +577,7 @@ extern "C" int irlb200_expected_svf(const irlb200_tables *t, int B, int causal,
     bt.phi_stride = mask_shared ? 0 : (size_t)t->S;
     bt.term_stride = mask_shared ? 0 : (size_t)t->S;
     bt.p0_stride = p0_shared ? 0 : (size_t)t->S;
-    bt.ef_stride = p0_shared ? 0 : (size_t)t->S;
+    bt.ef_stride = ef_shared ? 0 : (size_t)t->S;
     bt.n_iter = n_iter; bt.status = status; bt.policy_out = policy_out;
     return causal ? launch_step_cta<true>(bt, B, (cudaStream_t)stream)
                   : launch_step_cta<false>(bt, B, (cudaStream_t)stream);

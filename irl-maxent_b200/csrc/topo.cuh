@@ -22,15 +22,15 @@ namespace irlb200 {
 
 // ---------------------------------------------------------------------------
 struct CtaTopo {
-    double *buf[2];      // shared memory, S doubles each
+    double *buf0, *buf1; // shared memory, S doubles each (selected, never indexed: stays in registers)
     double *scratch;     // shared memory, 32 doubles
     int *flag;           // shared memory, 2 ints: sticky "a NaN diff was seen", by vote parity
     unsigned vseq;       // vote counter (same on every thread)
 
     __device__ __forceinline__ int rank() const { return threadIdx.x; }
     __device__ __forceinline__ int nthreads() const { return blockDim.x; }
-    __device__ __forceinline__ double load(int b, int i) const { return buf[b][i]; }
-    __device__ __forceinline__ void store(int b, int i, double v) const { buf[b][i] = v; }
+    __device__ __forceinline__ double load(int b, int i) const { return (b ? buf1 : buf0)[i]; }
+    __device__ __forceinline__ void store(int b, int i, double v) const { (b ? buf1 : buf0)[i] = v; }
     __device__ __forceinline__ void sync() { __syncthreads(); }
 
     __device__ __forceinline__ void begin_phase() {
@@ -61,7 +61,7 @@ struct GridSyncState {
 };
 
 struct GridTopo {
-    double *buf[2];             // global memory, S doubles each
+    double *buf0, *buf1;        // global memory, S doubles each
     GridSyncState *gs;
     unsigned seq;               // barrier sequence number (same on every thread)
     double *scratch;            // shared, 32 doubles
@@ -70,8 +70,8 @@ struct GridTopo {
 
     __device__ __forceinline__ int rank() const { return blockIdx.x * blockDim.x + threadIdx.x; }
     __device__ __forceinline__ int nthreads() const { return gridDim.x * blockDim.x; }
-    __device__ __forceinline__ double load(int b, int i) const { return ld_cg(buf[b] + i); }
-    __device__ __forceinline__ void store(int b, int i, double v) const { st_cg(buf[b] + i, v); }
+    __device__ __forceinline__ double load(int b, int i) const { return ld_cg((b ? buf1 : buf0) + i); }
+    __device__ __forceinline__ void store(int b, int i, double v) const { st_cg((b ? buf1 : buf0) + i, v); }
 
     __device__ __forceinline__ void begin_phase() {
         if (threadIdx.x == 0) *flag = 0;

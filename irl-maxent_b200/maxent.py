@@ -207,7 +207,7 @@ def irl_causal(p_transition, features, terminal, trajectories, optim, init, disc
 # -- batched mode (no counterpart in the reference: B independent problems) ------------
 
 def compute_expected_svf_batch(tables, p_initial, terminal, reward, eps=1e-5, causal=False,
-                               discount=None, eps_lap=1e-5, e_features=None, fused=None):
+                               discount=None, eps_lap=1e-5, e_features=None, fused=None, max_sweeps=None):
     """B independent gradient-step bodies in one or two launches.
 
     tables: `Tables` with 1 (shared) or B worlds; reward [B,S]; p_initial [S] or [B,S];
@@ -218,5 +218,5 @@ def compute_expected_svf_batch(tables, p_initial, terminal, reward, eps=1e-5, ca
     phi = E.terminal_phi(terminal, S) if causal else None
     d, g, _ = E.expected_svf(tables, p_initial, mask, reward, causal=causal, phi=phi,
                              discount=discount if causal else 0.0, eps_lap=eps_lap, eps_svf=eps,
-                             e_features=e_features, fused=fused)
+                             e_features=e_features, fused=fused, max_sweeps=max_sweeps)
     return d, g
