@@ -143,6 +143,127 @@ __global__ void __launch_bounds__(MAXT, 1) step_cta_kernel(const StepBatch bt) {
 }
 
 // ---------------------------------------------------------------------------
+// Hand-tuned forward pass for the register-resident shape (A = 4, Kp = 5).
+//
+// Same arithmetic, same order as svf_phase<CtaTopo, 4, 5, SPT> -- results are
+// bit-identical -- but the sweep body is stripped to what the FP64 pipe and the
+// issue slots must do:
+//   * the two iterate buffers sit STRIDE bytes apart (compile-time), the five
+//     gather addresses of every owned state are precomputed 32-bit shared
+//     addresses, so a sweep is 5 x (LDS.64 [addr + imm]; DFMA) per state with
+//     no address arithmetic at all;
+//   * states beyond S are padded with zero weights instead of predicated out;
+//   * the stop rule is one DSETP per state accumulated in a predicate
+//     (`!(|diff| <= eps)`, true for "greater" and for NaN) and one bar.red.or per
+//     sweep; whether a surviving vote came from a non-finite iterate is checked
+//     every 16 sweeps (such an iterate is sticky, so the loop ends within 16
+//     sweeps of the reference's NaN exit; convergent runs stop on exactly the
+//     reference's sweep).
+// ---------------------------------------------------------------------------
+// One sweep of the hand-tuned forward kernel: all gathers first, then SPT independent
+// DFMA chains (the compiler interleaves them, hiding the 8-cycle DFMA latency), then the
+// stores and the stop-rule predicates.  OFF_R / OFF_W select the iterate buffers.
+template <int SPT, int OFF_R, int OFF_W>
+__device__ __forceinline__ bool svf_fast_sweep(unsigned char *smem, const uint32_t (&ad)[SPT][5],
+                                               const uint32_t (&own)[SPT], const double (&w)[SPT][5],
+                                               const double (&p0r)[SPT], double (&cur)[SPT], double eps) {
+    double v[SPT][5], x[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) v[k][j] = *reinterpret_cast<const double *>(smem + ad[k][j] + OFF_R);
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+        double acc = fma(w[k][0], v[k][0], 0.0);
+        acc = fma(w[k][1], v[k][1], acc);
+        acc = fma(w[k][2], v[k][2], acc);
+        acc = fma(w[k][3], v[k][3], acc);
+        acc = fma(w[k][4], v[k][4], acc);
+        x[k] = p0r[k] + acc;                                            // p_initial + sum   maxent.py:110
+    }
+    bool go = false;
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+        *reinterpret_cast<double *>(smem + own[k] + OFF_W) = x[k];
+        go |= !(fabs(x[k] - cur[k]) <= eps);                            // |diff| > eps, or NaN
+        cur[k] = x[k];
+    }
+    return go;
+}
+
+template <int SPT, int STRIDE, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) svf_cta_fast_kernel(const SvfBatch bt) {
+    constexpr int K = 5, A = 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int *flag = reinterpret_cast<int *>(smem_raw + 2 * STRIDE);
+
+    SvfArgs a = bt.a;
+    offset_svf(a, bt, blockIdx.x);
+    const int S = a.S, T = blockDim.x, tid = threadIdx.x;
+
+    double w[SPT][K], p0r[SPT], cur[SPT];
+    uint32_t ad[SPT][K], own[SPT];          // byte offsets into the first iterate buffer
+
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+        const int s = tid + k * T;
+        const bool act = s < S;
+        own[k] = 8u * (uint32_t)s;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int pred = act ? a.idx[(size_t)j * S + s] : s;
+            double acc = 0.0;
+            if (act) {
+#pragma unroll
+                for (int aa = 0; aa < A; ++aa)
+                    acc = fma(__ldg(a.p + ((size_t)aa * K + j) * S + s), a.policy[(size_t)pred * A + aa], acc);
+                if (a.term[pred]) acc = 0.0;
+            }
+            w[k][j] = acc;
+            ad[k][j] = 8u * (uint32_t)pred;
+        }
+        p0r[k] = act ? a.p0[s] : 0.0;
+        cur[k] = 0.0;
+        *reinterpret_cast<double *>(smem_raw + own[k]) = 0.0;
+        *reinterpret_cast<double *>(smem_raw + own[k] + STRIDE) = 0.0;
+    }
+    if (tid == 0) *flag = 0;
+    __syncthreads();
+
+    const double eps = a.eps;
+    const int limit = a.max_sweeps > 0 ? a.max_sweeps : 0x7fffffff;
+    int n = 0, status = IRLB200_ST_CONVERGED;
+    for (;;) {
+        const bool go = (n & 1) ? svf_fast_sweep<SPT, STRIDE, 0>(smem_raw, ad, own, w, p0r, cur, eps)
+                                : svf_fast_sweep<SPT, 0, STRIDE>(smem_raw, ad, own, w, p0r, cur, eps);
+        ++n;
+        if (!__syncthreads_or(go ? 1 : 0)) break;                       // delta <= eps: converged
+        if ((n & 15) == 0) {                                            // did a vote survive on NaN?
+            bool bad = false;
+#pragma unroll
+            for (int k = 0; k < SPT; ++k) bad |= (cur[k] - cur[k]) != 0.0;   // NaN or +-inf iterate
+            if (bad) *flag = 1;     // an infinite iterate makes the next diff inf - inf = NaN
+            __syncthreads();
+            if (*flag) { status = IRLB200_ST_NONFINITE; break; }
+        }
+        if (n >= limit) { status = IRLB200_ST_MAXSWEEPS; break; }
+    }
+
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+        const int s = tid + k * T;
+        if (s < S) {
+            a.svf[s] = cur[k];
+            if (a.grad) a.grad[s] = a.e_features[s] - cur[k];
+        }
+    }
+    if (tid == 0) {
+        if (bt.n_iter) bt.n_iter[(size_t)blockIdx.x * bt.out_stride] = n;
+        if (bt.status) bt.status[(size_t)blockIdx.x * bt.out_stride] = status;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // grid (cooperative) kernels -- one problem
 // ---------------------------------------------------------------------------
 struct GridWork {
@@ -244,23 +365,25 @@ static int launch_svf_cta(SvfBatch bt, int B, cudaStream_t st) {
     const int force_stream = env_int("IRLB200_FORCE_STREAMED", 0);
     const int spt_pref = env_int("IRLB200_SVF_SPT", 0);
     if (fast && !force_stream && S <= 4096) {
-        int spt = spt_pref ? spt_pref : (S <= 256 ? 1 : (S <= 2048 ? 2 : 4));
-        if (spt == 1 && S > 1024) spt = 2;
-        if (spt == 2 && S > 2048) spt = 4;
+        // hand-tuned kernel; (states per thread, buffer stride) picked by size.  The block is
+        // ceil(S / SPT) threads rounded to a warp; padded states carry zero weights.
+        int spt = spt_pref ? spt_pref : (S <= 128 ? 1 : (S <= 2048 ? 2 : 4));
         bt.a.w_scratch = nullptr;
-        if (spt == 1) {
-            auto k = svf_cta_kernel<4, 5, 1, 1024, 1>;
-            if (int rc = prep_smem(k, smem)) return rc;
-            k<<<B, round_up32(S), smem, st>>>(bt);
-        } else if (spt == 2) {
-            auto k = svf_cta_kernel<4, 5, 2, 1024, 1>;
-            if (int rc = prep_smem(k, smem)) return rc;
-            k<<<B, round_up32((S + 1) / 2), smem, st>>>(bt);
+#define SVF_FAST(SPT_, STRIDE_, MAXT_, MINB_)                                               \
+    do {                                                                                    \
+        auto k = svf_cta_fast_kernel<SPT_, STRIDE_, MAXT_, MINB_>;                          \
+        const size_t sm = 2 * (size_t)(STRIDE_) + 16;                                       \
+        if (int rc = prep_smem(k, sm)) return rc;                                           \
+        k<<<B, round_up32((S + (SPT_) - 1) / (SPT_)), sm, st>>>(bt);                        \
+    } while (0)
+        if (S <= 256) {
+            if (spt == 1) SVF_FAST(1, 2048, 256, 1); else if (spt == 2) SVF_FAST(2, 2048, 128, 1); else SVF_FAST(4, 2048, 64, 1);
+        } else if (S <= 1024) {
+            if (spt == 1) SVF_FAST(1, 8192, 1024, 1); else if (spt == 2) SVF_FAST(2, 8192, 512, 2); else SVF_FAST(4, 8192, 256, 2);
         } else {
-            auto k = svf_cta_kernel<4, 5, 4, 1024, 1>;
-            if (int rc = prep_smem(k, smem)) return rc;
-            k<<<B, round_up32((S + 3) / 4), smem, st>>>(bt);
+            if (spt <= 2 && S <= 2048) SVF_FAST(2, 32768, 1024, 1); else SVF_FAST(4, 32768, 1024, 1);
         }
+#undef SVF_FAST
     } else {
         if (A > kMaxDynA) return fail(IRLB200_EINVAL, "run-time A > 16 is not supported");
         double *ws = nullptr;

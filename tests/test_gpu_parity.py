@@ -236,7 +236,9 @@ def test_guards_and_status(golden):
     E.svf(t, g["k5_p0"], E.terminal_mask([24], 25), pol, 1e-5)
     assert E.last_info.stati()[0] == E.ST_NONFINITE
     d_ref, n_ref = D.expected_svf_from_policy(P, g["k5_p0"], [24], pol)
-    assert counts()[0] <= n_ref + 8     # dense 0*NaN poisons at once, sparse needs a few hops
+    # the reference's dense 0*NaN poisons every state in the first sweep; the sparse gather needs a
+    # few hops, and the register-resident kernel looks for a non-finite iterate every 16 sweeps
+    assert counts()[0] <= n_ref + 16
 
 
 # ------------------------------------------------------------- public API ---
