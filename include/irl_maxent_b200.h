@@ -94,6 +94,12 @@ int irlb200_gridworld_tables(int size, int icy, int B, const double *p_slip,
                              int32_t *succ_idx, double *succ_p,
                              int32_t *pred_idx, double *pred_p, void *stream);
 
+/* Rows of the states [lo, lo+cnt) of ONE world only: arrays of stride cnt holding GLOBAL neighbour
+ * indices (slab mode: every rank builds just its own rows; 2048x2048 never exists densely). */
+int irlb200_gridworld_tables_range(int size, int icy, double p_slip, int lo, int cnt,
+                                   int32_t *succ_idx, double *succ_p,
+                                   int32_t *pred_idx, double *pred_p, void *stream);
+
 /* Dense P[S][S][A] of the same worlds, written on the device (test helper for the
  * compression kernels at sizes where the Python table builder is too slow). */
 int irlb200_gridworld_dense(int size, int icy, double p_slip, double *P, void *stream);
@@ -177,6 +183,25 @@ int irlb200_expected_svf(const irlb200_tables *t, int B, int causal,
                          int max_sweeps, double *svf, const double *e_features, int ef_shared,
                          double *grad, double *policy_out /* [B][S][A] or NULL */,
                          int32_t *n_iter, int32_t *status, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * slab mode (one huge MDP sharded by contiguous state ranges over several GPUs; the halo
+ * exchange and the convergence all-reduce run between launches, see irl-maxent_b200/slab.py).
+ * ONE sweep over the owned states [lo, lo+cnt) of a full-length iterate:
+ *   op 1: soft-VI sweep (maxent.py:329-338), p = succ_p [A][K][cnt], c0 = reward, c1 = phi
+ *   op 2: value-iteration sweep (solver.py:44-50),  p = succ_p, c0 = reward
+ *   op 3: forward sweep (maxent.py:109-112),        p = W [K][cnt] from irlb200_slab_weights, c0 = p_initial
+ *   idx [K][cnt] holds global indices; c0/c1/policy are local (length cnt); x_in / x_out are
+ *   full-length, only x_out[lo..lo+cnt) is written.  vote[0] |= (some |diff| > eps),
+ *   vote[1] |= (some diff is NaN).  policy ([cnt][A] or NULL, op 1): exp(q - v) of this sweep (:341).
+ * ------------------------------------------------------------------------- */
+int irlb200_slab_sweep(int op, int lo, int cnt, int A, int K, const int32_t *idx, const double *p,
+                       const double *c0, const double *c1, double discount, double eps, int vi_mean,
+                       const double *x_in, double *x_out, int32_t *vote, double *policy, void *stream);
+/* W[j][i] = sum_a pred_p[a][j][i] * policy[pred][a] (0 if pred terminal); policy [S_total][A] and
+ * terminal_mask [S_total] are globally indexed (ghost rows exchanged by the caller). */
+int irlb200_slab_weights(int cnt, int A, int K, const int32_t *pred_idx, const double *pred_p,
+                         const double *policy, const uint8_t *terminal_mask, double *W, void *stream);
 
 /* ------------------------------------------------------------------------- *
  * dense feature products on the path: reward = features . theta (maxent.py:244)

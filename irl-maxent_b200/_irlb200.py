@@ -53,6 +53,9 @@ SIGNATURES = {
     "irlb200_dense_fill": ([_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "irlb200_gridworld_tables": ([_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "irlb200_gridworld_dense": ([_i, _i, _d, _vp, _vp], _i),
+    "irlb200_gridworld_tables_range": ([_i, _i, _d, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
+    "irlb200_slab_sweep": ([_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _d, _d, _i, _vp, _vp, _vp, _vp, _vp], _i),
+    "irlb200_slab_weights": ([_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "irlb200_backward": ([_tp, _i, _vp, _vp, _i, _i, _vp, _i, _vp], _i),
     "irlb200_soft_vi": ([_tp, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _i, _vp], _i),
     "irlb200_value_iteration": ([_tp, _i, _vp, _d, _d, _i, _i, _vp, _vp, _vp, _i, _vp], _i),

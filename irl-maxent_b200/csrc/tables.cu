@@ -142,20 +142,25 @@ __device__ double world_prob(int n, int icy, double p, int s_from, int s_to, int
     return 0.0;
 }
 
+// Rows of the states [lo, lo + cnt) only (cnt == S, lo == 0: the whole world); the arrays have
+// stride cnt and hold GLOBAL neighbour indices.  p_slip_scalar is used when p_slip == nullptr.
 __global__ void gridworld_tables_kernel(int n, int icy, int B, const double *__restrict__ p_slip,
+                                        double p_slip_scalar, int lo, int cnt,
                                         int32_t *succ_idx, double *succ_p,
                                         int32_t *pred_idx, double *pred_p) {
     constexpr int K = 5, A = 4;
-    const int S = n * n;
+    const int S = cnt;                       // stride of the output arrays
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)B * S) return;
-    const int b = (int)(gid / S), s = (int)(gid % S);
-    const double p = icy ? p_slip[b] : 0.0;
+    const int b = (int)(gid / S), sl = (int)(gid % S);
+    const double p = icy ? (p_slip ? p_slip[b] : p_slip_scalar) : 0.0;
     int32_t *si = succ_idx + (size_t)b * K * S, *pi = pred_idx + (size_t)b * K * S;
     double *sp = succ_p + (size_t)b * A * K * S, *pp = pred_p + (size_t)b * A * K * S;
-    const int x = s % n, y = s / n;
+    const int sg = lo + sl;                  // global state
+    const int x = sg % n, y = sg / n;
     // candidate neighbours in ascending state order
-    const int cand[5] = {s - n, s - 1, s, s + 1, s + n};
+    const int cand[5] = {sg - n, sg - 1, sg, sg + 1, sg + n};
+    const int s = sl;                        // local slot column
     const bool ok[5] = {y > 0, x > 0, true, x < n - 1, y < n - 1};
     int js = 0, jp = 0;
     for (int c = 0; c < 5; ++c) {
@@ -164,8 +169,8 @@ __global__ void gridworld_tables_kernel(int n, int icy, int B, const double *__r
         double ps[A], pq[A];
         bool nzs = false, nzp = false;
         for (int a = 0; a < A; ++a) {
-            ps[a] = world_prob(n, icy, p, s, t, a);     // s -> t
-            pq[a] = world_prob(n, icy, p, t, s, a);     // t -> s
+            ps[a] = world_prob(n, icy, p, sg, t, a);    // s -> t
+            pq[a] = world_prob(n, icy, p, t, sg, a);    // t -> s
             nzs |= ps[a] != 0.0;
             nzp |= pq[a] != 0.0;
         }
@@ -181,11 +186,11 @@ __global__ void gridworld_tables_kernel(int n, int icy, int B, const double *__r
         }
     }
     for (; js < K; ++js) {
-        si[(size_t)js * S + s] = s;
+        si[(size_t)js * S + s] = sg;
         for (int a = 0; a < A; ++a) sp[((size_t)a * K + js) * S + s] = 0.0;
     }
     for (; jp < K; ++jp) {
-        pi[(size_t)jp * S + s] = s;
+        pi[(size_t)jp * S + s] = sg;
         for (int a = 0; a < A; ++a) pp[((size_t)a * K + jp) * S + s] = 0.0;
     }
 }
@@ -297,9 +302,23 @@ extern "C" int irlb200_gridworld_tables(int size, int icy, int B, const double *
     const long long total = (long long)B * size * size;
     const long long blocks = (total + 255) / 256;
     if (blocks > 0x7fffffffLL) return fail(IRLB200_EINVAL, "gridworld_tables: batch too large");
-    gridworld_tables_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(size, icy, B, p_slip, succ_idx,
-                                                                               succ_p, pred_idx, pred_p);
+    gridworld_tables_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        size, icy, B, p_slip, 0.0, 0, size * size, succ_idx, succ_p, pred_idx, pred_p);
     CHECK_LAUNCH("gridworld_tables_kernel");
+    return IRLB200_OK;
+}
+
+extern "C" int irlb200_gridworld_tables_range(int size, int icy, double p_slip, int lo, int cnt,
+                                              int32_t *succ_idx, double *succ_p,
+                                              int32_t *pred_idx, double *pred_p, void *stream) {
+    if (size <= 0 || cnt <= 0 || lo < 0 || (long long)lo + cnt > (long long)size * size ||
+        !succ_idx || !succ_p || !pred_idx || !pred_p)
+        return fail(IRLB200_EINVAL, "gridworld_tables_range: bad argument");
+    if ((long long)size * size > 0x7fffffffLL) return fail(IRLB200_EINVAL, "gridworld_tables_range: S >= 2^31");
+    if (device_count_impl() <= 0) return fail(IRLB200_ECUDA, "no CUDA device");
+    gridworld_tables_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        size, icy, 1, nullptr, p_slip, lo, cnt, succ_idx, succ_p, pred_idx, pred_p);
+    CHECK_LAUNCH("gridworld_tables_kernel<range>");
     return IRLB200_OK;
 }
 
