@@ -115,6 +115,11 @@ typedef struct irlb200_tables {
     const int32_t *pred_idx;  /* [B or 1][Kp][S]                                          */
     const double  *pred_p;    /* [B or 1][A][Kp][S]                                       */
     int32_t shared;           /* 1: one table for the whole batch, 0: one table per problem */
+    int32_t stencil_n;        /* > 0: the caller asserts that S = n*n and every table entry with
+                                 non-zero probability links s to one of s-n, s-1, s, s+1, s+n without
+                                 wrapping around a row end (any GridWorld / IcyGridWorld; checked by
+                                 the host layer when tables are built).  Enables the stencil-tiled
+                                 kernels; 0 = no assumption, generic gather.                        */
 } irlb200_tables;
 
 /* ------------------------------------------------------------------------- *

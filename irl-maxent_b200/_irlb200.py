@@ -34,7 +34,7 @@ class _CTables(ctypes.Structure):
                 ("Ks", ctypes.c_int32), ("Kp", ctypes.c_int32),
                 ("succ_idx", ctypes.c_void_p), ("succ_p", ctypes.c_void_p),
                 ("pred_idx", ctypes.c_void_p), ("pred_p", ctypes.c_void_p),
-                ("shared", ctypes.c_int32)]
+                ("shared", ctypes.c_int32), ("stencil_n", ctypes.c_int32)]
 
 
 _lib = None
@@ -143,10 +143,12 @@ class Tables:
     succ_p [Bt][A][Ks][S] f64, pred_idx [Bt][Kp][S], pred_p [Bt][A][Kp][S].
     """
 
-    def __init__(self, S, A, Ks, Kp, succ_idx, succ_p, pred_idx, pred_p, n_tables=1):
+    def __init__(self, S, A, Ks, Kp, succ_idx, succ_p, pred_idx, pred_p, n_tables=1, stencil_n=0):
         self.S, self.A, self.Ks, self.Kp = int(S), int(A), int(Ks), int(Kp)
         self.succ_idx, self.succ_p, self.pred_idx, self.pred_p = succ_idx, succ_p, pred_idx, pred_p
         self.n_tables = int(n_tables)
+        # > 0: S = n*n and all links stay within {s-n, s-1, s, s+1, s+n} without wrapping a row end
+        self.stencil_n = int(stencil_n)
 
     # the reference's `n_states, _, n_actions = p_transition.shape` keeps working on a handle
     @property
@@ -155,7 +157,7 @@ class Tables:
 
     def c_struct(self, shared):
         return _CTables(self.S, self.A, self.Ks, self.Kp, self.succ_idx.data_ptr(), self.succ_p.data_ptr(),
-                        self.pred_idx.data_ptr(), self.pred_p.data_ptr(), 1 if shared else 0)
+                        self.pred_idx.data_ptr(), self.pred_p.data_ptr(), 1 if shared else 0, self.stencil_n)
 
     def nbytes(self):
         return sum(t.numel() * t.element_size() for t in (self.succ_idx, self.succ_p, self.pred_idx, self.pred_p))
@@ -163,7 +165,25 @@ class Tables:
     def select(self, b):
         """Handle on the tables of world b of a batch (views, no copy)."""
         return Tables(self.S, self.A, self.Ks, self.Kp, self.succ_idx[b:b + 1], self.succ_p[b:b + 1],
-                      self.pred_idx[b:b + 1], self.pred_p[b:b + 1], 1)
+                      self.pred_idx[b:b + 1], self.pred_p[b:b + 1], 1, self.stencil_n)
+
+    def detect_stencil(self):
+        """Set stencil_n if the tables have the 5-point grid structure (torch ops, once per table)."""
+        torch = _torch()
+        n = int(round(self.S ** 0.5))
+        self.stencil_n = 0
+        if n * n != self.S or n < 2 or self.A != 4 or self.Ks != 5 or self.Kp != 5:
+            return 0
+        s = torch.arange(self.S, device=self.succ_idx.device, dtype=torch.int64)
+        x = s % n
+        for idx, p in ((self.succ_idx, self.succ_p), (self.pred_idx, self.pred_p)):
+            off = idx.to(torch.int64) - s                      # [Bt, K, S]
+            used = (p != 0).any(dim=1)                         # [Bt, K, S]
+            ok = (off == 0) | (off == n) | (off == -n) | ((off == 1) & (x < n - 1)) | ((off == -1) & (x > 0))
+            if not bool((ok | ~used).all()):
+                return 0
+        self.stencil_n = n
+        return n
 
 
 def _round_slots(A, k):
@@ -194,6 +214,7 @@ def compress_dense(p_transition):
                                    _ptr(pred_p), _ptr(pred_cnt), _stream()))
     t = Tables(S, A, Ks, Kp, succ_idx, succ_p, pred_idx, pred_p, 1)
     t.k_discovered = (ks, kp)
+    t.detect_stencil()
     return t
 
 
@@ -215,7 +236,7 @@ def gridworld_tables(size, p_slip=None, icy=True):
     pred_p = torch.empty((B, A, K, S), dtype=torch.float64, device=dev)
     _check(_lib.irlb200_gridworld_tables(size, 1 if icy else 0, B, _ptr(ps_d), _ptr(succ_idx), _ptr(succ_p),
                                          _ptr(pred_idx), _ptr(pred_p), _stream()))
-    return Tables(S, A, K, K, succ_idx, succ_p, pred_idx, pred_p, B)
+    return Tables(S, A, K, K, succ_idx, succ_p, pred_idx, pred_p, B, stencil_n=size if size >= 2 else 0)
 
 
 def gridworld_dense(size, p_slip=0.2, icy=True):

@@ -52,6 +52,7 @@ struct SvfArgs {
     const uint8_t *term;         // [S]
     const double *policy;        // [S][A] (generic address)
     double *w_scratch;           // [K][S] global scratch, streamed flavour only
+    int grid_n;                  // > 0: predecessor offsets lie in {-n,-1,0,+1,+n} (grid stencil), n = grid_n
     double eps;
     int max_sweeps;
     double *svf;                 // [S] out

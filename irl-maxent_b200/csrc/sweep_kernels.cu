@@ -264,6 +264,176 @@ __global__ void __launch_bounds__(MAXT, MINB) svf_cta_fast_kernel(const SvfBatch
 }
 
 // ---------------------------------------------------------------------------
+// Stencil-tiled forward pass for grid worlds (predecessor offsets within {-n,-1,0,+1,+n}).
+//
+// The generic gather above is bound by the shared-memory datapath: 5 LDS.64 per state =
+// 384 wavefronts per 1 024-state sweep against 141 FP64-pipe cycles.  Here a thread owns a
+// TY x TX tile of grid cells and keeps their iterate values in registers; only the halo of
+// the tile (TX cells above / below, TY cells left / right) is read from shared memory:
+// (2 TX + 2 TY) / (TX TY) loads per state (1.5 for 2 x 4, 1.0 for 4 x 4).  Every thread
+// publishes its tile in a private slot of PITCH = TX TY + 1 doubles; the odd pitch makes
+// the 64-bit accesses of a half-warp hit distinct banks, and a cell's offset inside the
+// slot is an immediate.
+//
+// Arithmetic: per state the same ascending-neighbour FMA chain as the ELL kernels
+// (s-n, s-1, s, s+1, s+n); a neighbour that is absent from the table enters as
+// fma(0, v, acc) == acc, so results are bit-identical to svf_cta_fast_kernel.
+// ---------------------------------------------------------------------------
+template <int TY, int TX, int MAXT>
+struct Grid5Cfg {
+    static constexpr int C = TY * TX;
+    static constexpr int PITCH = C + 1 + ((C + 1) % 2 == 0 ? 1 : 0);     // odd number of doubles
+    static constexpr int STRIDE = MAXT * PITCH * 8;                      // bytes between the two buffers
+};
+
+template <int TY, int TX, int MAXT, int OFF_R, int OFF_W>
+__device__ __forceinline__ bool svf_grid5_sweep(unsigned char *smem, uint32_t own, uint32_t nb_up, uint32_t nb_dn,
+                                                uint32_t nb_lf, uint32_t nb_rt, const double (&w)[TY * TX][5],
+                                                const double (&p0r)[TY * TX], double (&cur)[TY * TX], double eps) {
+    double up[TX], dn[TX], lf[TY], rt[TY], x[TY * TX];
+#pragma unroll
+    for (int ix = 0; ix < TX; ++ix) {
+        up[ix] = *reinterpret_cast<const double *>(smem + nb_up + 8 * ((TY - 1) * TX + ix) + OFF_R);
+        dn[ix] = *reinterpret_cast<const double *>(smem + nb_dn + 8 * ix + OFF_R);
+    }
+#pragma unroll
+    for (int iy = 0; iy < TY; ++iy) {
+        lf[iy] = *reinterpret_cast<const double *>(smem + nb_lf + 8 * (iy * TX + TX - 1) + OFF_R);
+        rt[iy] = *reinterpret_cast<const double *>(smem + nb_rt + 8 * (iy * TX) + OFF_R);
+    }
+#pragma unroll
+    for (int iy = 0; iy < TY; ++iy)
+#pragma unroll
+        for (int ix = 0; ix < TX; ++ix) {
+            const int c = iy * TX + ix;
+            const double v_up = iy > 0 ? cur[c - TX] : up[ix];
+            const double v_lf = ix > 0 ? cur[c - 1] : lf[iy];
+            const double v_rt = ix < TX - 1 ? cur[c + 1] : rt[iy];
+            const double v_dn = iy < TY - 1 ? cur[c + TX] : dn[ix];
+            double acc = fma(w[c][0], v_up, 0.0);
+            acc = fma(w[c][1], v_lf, acc);
+            acc = fma(w[c][2], cur[c], acc);
+            acc = fma(w[c][3], v_rt, acc);
+            acc = fma(w[c][4], v_dn, acc);
+            x[c] = p0r[c] + acc;                                        // p_initial + sum   maxent.py:110
+        }
+    bool go = false;
+#pragma unroll
+    for (int c = 0; c < TY * TX; ++c) {
+        *reinterpret_cast<double *>(smem + own + 8 * c + OFF_W) = x[c];
+        go |= !(fabs(x[c] - cur[c]) <= eps);                            // |diff| > eps, or NaN
+        cur[c] = x[c];
+    }
+    return go;
+}
+
+template <int TY, int TX, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) svf_grid5_kernel(const SvfBatch bt, const int n) {
+    using Cfg = Grid5Cfg<TY, TX, MAXT>;
+    constexpr int C = Cfg::C, K = 5, A = 4, STRIDE = Cfg::STRIDE;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int *flag = reinterpret_cast<int *>(smem_raw + 2 * STRIDE);
+
+    SvfArgs a = bt.a;
+    offset_svf(a, bt, blockIdx.x);
+    const int S = a.S, tid = threadIdx.x;
+    const int ntx = n / TX, nty = n / TY;
+    const bool live = tid < ntx * nty;
+    const int tx = live ? tid % ntx : 0, ty = live ? tid / ntx : 0;
+
+    double w[C][5], p0r[C], cur[C];
+    const uint32_t slot = 8u * Cfg::PITCH;
+    const uint32_t own = slot * tid;
+    const uint32_t nb_up = (live && ty > 0) ? own - slot * ntx : own;
+    const uint32_t nb_dn = (live && ty < nty - 1) ? own + slot * ntx : own;
+    const uint32_t nb_lf = (live && tx > 0) ? own - slot : own;
+    const uint32_t nb_rt = (live && tx < ntx - 1) ? own + slot : own;
+
+#pragma unroll
+    for (int iy = 0; iy < TY; ++iy)
+#pragma unroll
+        for (int ix = 0; ix < TX; ++ix) {
+            const int c = iy * TX + ix;
+            const int s = (ty * TY + iy) * n + tx * TX + ix;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) w[c][k] = 0.0;
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const int pred = a.idx[(size_t)j * S + s];
+                    double acc = 0.0;
+#pragma unroll
+                    for (int aa = 0; aa < A; ++aa)
+                        acc = fma(__ldg(a.p + ((size_t)aa * K + j) * S + s), a.policy[(size_t)pred * A + aa], acc);
+                    if (a.term[pred]) acc = 0.0;
+                    const int off = pred - s;
+                    // at most one table entry per offset carries weight; padding entries add +0
+                    w[c][0] += (off == -n) ? acc : 0.0;
+                    w[c][1] += (off == -1) ? acc : 0.0;
+                    w[c][2] += (off == 0) ? acc : 0.0;
+                    w[c][3] += (off == 1) ? acc : 0.0;
+                    w[c][4] += (off == n) ? acc : 0.0;
+                }
+            }
+            p0r[c] = live ? a.p0[s] : 0.0;
+            cur[c] = 0.0;
+            *reinterpret_cast<double *>(smem_raw + own + 8 * c) = 0.0;
+            *reinterpret_cast<double *>(smem_raw + own + 8 * c + STRIDE) = 0.0;
+        }
+    if (tid == 0) *flag = 0;
+    __syncthreads();
+
+    const double eps = a.eps;
+    const int limit = a.max_sweeps > 0 ? a.max_sweeps : 0x7fffffff;
+    int nsw = 0, status = IRLB200_ST_CONVERGED;
+    for (;;) {
+        const bool go = (nsw & 1)
+            ? svf_grid5_sweep<TY, TX, MAXT, STRIDE, 0>(smem_raw, own, nb_up, nb_dn, nb_lf, nb_rt, w, p0r, cur, eps)
+            : svf_grid5_sweep<TY, TX, MAXT, 0, STRIDE>(smem_raw, own, nb_up, nb_dn, nb_lf, nb_rt, w, p0r, cur, eps);
+        ++nsw;
+        if (!__syncthreads_or(go ? 1 : 0)) break;
+        if ((nsw & 15) == 0) {
+            bool bad = false;
+#pragma unroll
+            for (int c = 0; c < C; ++c) bad |= (cur[c] - cur[c]) != 0.0;
+            if (bad) *flag = 1;
+            __syncthreads();
+            if (*flag) { status = IRLB200_ST_NONFINITE; break; }
+        }
+        if (nsw >= limit) { status = IRLB200_ST_MAXSWEEPS; break; }
+    }
+
+    if (live) {
+#pragma unroll
+        for (int iy = 0; iy < TY; ++iy)
+#pragma unroll
+            for (int ix = 0; ix < TX; ++ix) {
+                const int c = iy * TX + ix;
+                const int s = (ty * TY + iy) * n + tx * TX + ix;
+                a.svf[s] = cur[c];
+                if (a.grad) a.grad[s] = a.e_features[s] - cur[c];
+            }
+    }
+    if (tid == 0) {
+        if (bt.n_iter) bt.n_iter[(size_t)blockIdx.x * bt.out_stride] = nsw;
+        if (bt.status) bt.status[(size_t)blockIdx.x * bt.out_stride] = status;
+    }
+}
+
+template <class Kern> static int prep_smem(Kern k, size_t bytes);
+static inline int round_up32(int x);
+template <int TY, int TX, int MAXT, int MINB>
+static int launch_svf_grid5(const SvfBatch &bt, int B, int n, cudaStream_t st) {
+    using Cfg = Grid5Cfg<TY, TX, MAXT>;
+    auto k = svf_grid5_kernel<TY, TX, MAXT, MINB>;
+    const size_t sm = 2 * (size_t)Cfg::STRIDE + 16;
+    if (int rc = prep_smem(k, sm)) return rc;
+    const int threads = round_up32((n / TX) * (n / TY));
+    k<<<B, threads, sm, st>>>(bt, n);
+    return IRLB200_OK;
+}
+
+// ---------------------------------------------------------------------------
 // grid (cooperative) kernels -- one problem
 // ---------------------------------------------------------------------------
 struct GridWork {
@@ -364,6 +534,25 @@ static int launch_svf_cta(SvfBatch bt, int B, cudaStream_t st) {
     const bool fast = is_fast_shape(A, K);
     const int force_stream = env_int("IRLB200_FORCE_STREAMED", 0);
     const int spt_pref = env_int("IRLB200_SVF_SPT", 0);
+    const int gn = bt.a.grid_n;
+    const int tile = env_int("IRLB200_SVF_TILE", 24);       // TY*10 + TX; 0 disables the tiled kernels
+    if (fast && !force_stream && gn > 0 && tile > 0 && gn * gn == S) {
+        bt.a.w_scratch = nullptr;
+        int rc = -100;
+        if (tile == 24 && gn % 4 == 0 && gn % 2 == 0 && (gn / 4) * (gn / 2) <= 128) rc = launch_svf_grid5<2, 4, 128, 3>(bt, B, gn, st);
+        else if (tile == 124 && gn % 4 == 0 && (gn / 4) * (gn / 2) <= 128) rc = launch_svf_grid5<2, 4, 128, 4>(bt, B, gn, st);
+        else if (tile == 142 && gn % 4 == 0 && (gn / 2) * (gn / 4) <= 128) rc = launch_svf_grid5<4, 2, 128, 4>(bt, B, gn, st);
+        else if (tile == 24 && gn % 4 == 0 && (gn / 4) * (gn / 2) <= 512) rc = launch_svf_grid5<2, 4, 512, 1>(bt, B, gn, st);
+        else if (tile == 44 && gn % 4 == 0 && (gn / 4) * (gn / 4) <= 64) rc = launch_svf_grid5<4, 4, 64, 4>(bt, B, gn, st);
+        else if (tile == 44 && gn % 4 == 0 && (gn / 4) * (gn / 4) <= 256) rc = launch_svf_grid5<4, 4, 256, 1>(bt, B, gn, st);
+        else if (tile == 22 && gn % 2 == 0 && (gn / 2) * (gn / 2) <= 256) rc = launch_svf_grid5<2, 2, 256, 2>(bt, B, gn, st);
+        else if (tile == 42 && gn % 4 == 0 && (gn / 2) * (gn / 4) <= 128) rc = launch_svf_grid5<4, 2, 128, 3>(bt, B, gn, st);
+        if (rc != -100) {
+            if (rc) return rc;
+            LAUNCH_CHECK("svf_grid5_kernel");
+            return IRLB200_OK;
+        }
+    }
     if (fast && !force_stream && S <= 4096) {
         // hand-tuned kernel; (states per thread, buffer stride) picked by size.  The block is
         // ceil(S / SPT) threads rounded to a warp; padded states carry zero weights.
@@ -648,6 +837,7 @@ static void fill_svf(SvfArgs &a, const irlb200_tables *t) {
     a = SvfArgs{};
     a.S = t->S; a.A = t->A; a.K = t->Kp;
     a.idx = t->pred_idx; a.p = t->pred_p;
+    a.grid_n = t->stencil_n;
 }
 
 extern "C" int irlb200_svf(const irlb200_tables *t, int B, const double *p_initial, int p0_shared,
