@@ -39,6 +39,7 @@ struct SuccArgs {
     int n_sweeps;                // backward: fixed sweep count (reference: 2*S)
     int max_sweeps;              // <= 0: unguarded
     int vi_mean;                 // VI: 1 = average over actions (solver.py:100)
+    int grid_n;                  // > 0: successor offsets lie in {-n,-1,0,+1,+n} (grid stencil)
     double *policy;              // [S][A] out (generic address: shared or global) or null
     double *policy2;             // optional second copy (global) or null
     double *value;               // [S] out (global) or null

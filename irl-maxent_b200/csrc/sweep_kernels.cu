@@ -420,6 +420,166 @@ __global__ void __launch_bounds__(MAXT, MINB) svf_grid5_kernel(const SvfBatch bt
     }
 }
 
+// ---------------------------------------------------------------------------
+// Stencil-tiled non-causal backward pass (local_action_probabilities, maxent.py:119-159).
+//
+// All but the last of the n_sweeps partition sweeps only carry zs forward, and
+//     zs'[s] = sum_a er[s] * sum_j P[s,j,a] * zs[j]  =  sum_j (er[s] * sum_a P[s,j,a]) * zs[j]
+// is a 5-weight stencil exactly like the forward sweep: 5 FMA per state instead of 20 FMA +
+// 4 MUL + 3 ADD (the FP64 pipe is what bounds these kernels).  The merged weights are formed
+// once, so the iterate differs from the reference's by rounding only (~1e-15 relative, checked
+// against the reference fixtures to 1e-10).  The LAST sweep is evaluated exactly as the
+// reference does (per-action za = er * P_a.dot(zs), zs = za.sum, policy = za / zs, :155-159)
+// from the ELL rows.  Range extension: exact power-of-two rescale every R sweeps.
+// ---------------------------------------------------------------------------
+template <int TY, int TX, int MAXT, int OFF_R, int OFF_W>
+__device__ __forceinline__ double lin_grid5_sweep(unsigned char *smem, uint32_t own, uint32_t nb_up, uint32_t nb_dn,
+                                                  uint32_t nb_lf, uint32_t nb_rt, const double (&w)[TY * TX][5],
+                                                  double (&cur)[TY * TX]) {
+    double up[TX], dn[TX], lf[TY], rt[TY], x[TY * TX];
+#pragma unroll
+    for (int ix = 0; ix < TX; ++ix) {
+        up[ix] = *reinterpret_cast<const double *>(smem + nb_up + 8 * ((TY - 1) * TX + ix) + OFF_R);
+        dn[ix] = *reinterpret_cast<const double *>(smem + nb_dn + 8 * ix + OFF_R);
+    }
+#pragma unroll
+    for (int iy = 0; iy < TY; ++iy) {
+        lf[iy] = *reinterpret_cast<const double *>(smem + nb_lf + 8 * (iy * TX + TX - 1) + OFF_R);
+        rt[iy] = *reinterpret_cast<const double *>(smem + nb_rt + 8 * (iy * TX) + OFF_R);
+    }
+    double m = 0.0;
+#pragma unroll
+    for (int iy = 0; iy < TY; ++iy)
+#pragma unroll
+        for (int ix = 0; ix < TX; ++ix) {
+            const int c = iy * TX + ix;
+            const double v_up = iy > 0 ? cur[c - TX] : up[ix];
+            const double v_lf = ix > 0 ? cur[c - 1] : lf[iy];
+            const double v_rt = ix < TX - 1 ? cur[c + 1] : rt[iy];
+            const double v_dn = iy < TY - 1 ? cur[c + TX] : dn[ix];
+            double acc = fma(w[c][0], v_up, 0.0);
+            acc = fma(w[c][1], v_lf, acc);
+            acc = fma(w[c][2], cur[c], acc);
+            acc = fma(w[c][3], v_rt, acc);
+            acc = fma(w[c][4], v_dn, acc);
+            x[c] = acc;
+        }
+#pragma unroll
+    for (int c = 0; c < TY * TX; ++c) {
+        *reinterpret_cast<double *>(smem + own + 8 * c + OFF_W) = x[c];
+        cur[c] = x[c];
+        m = fmax(m, x[c]);
+    }
+    return m;
+}
+
+template <int TY, int TX, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) backward_grid5_kernel(const SuccBatch bt, const int n) {
+    using Cfg = Grid5Cfg<TY, TX, MAXT>;
+    constexpr int C = Cfg::C, K = 5, A = 4, STRIDE = Cfg::STRIDE;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *scratch = reinterpret_cast<double *>(smem_raw + 2 * STRIDE);      // 32 doubles
+    double *lin = reinterpret_cast<double *>(smem_raw + 2 * STRIDE + 256);    // S doubles: zs by state index
+
+    SuccArgs a = bt.a;
+    offset_succ(a, bt, blockIdx.x);
+    const int S = a.S, tid = threadIdx.x;
+    const int ntx = n / TX, nty = n / TY;
+    const bool live = tid < ntx * nty;
+    const int tx = live ? tid % ntx : 0, ty = live ? tid / ntx : 0;
+
+    double w[C][5], cur[C];
+    const uint32_t slot = 8u * Cfg::PITCH;
+    const uint32_t own = slot * tid;
+    const uint32_t nb_up = (live && ty > 0) ? own - slot * ntx : own;
+    const uint32_t nb_dn = (live && ty < nty - 1) ? own + slot * ntx : own;
+    const uint32_t nb_lf = (live && tx > 0) ? own - slot : own;
+    const uint32_t nb_rt = (live && tx < ntx - 1) ? own + slot : own;
+
+    double max_abs_r = 0.0;
+#pragma unroll
+    for (int iy = 0; iy < TY; ++iy)
+#pragma unroll
+        for (int ix = 0; ix < TX; ++ix) {
+            const int c = iy * TX + ix;
+            const int s = (ty * TY + iy) * n + tx * TX + ix;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) w[c][k] = 0.0;
+            double z0 = 0.0;
+            if (live) {
+                const double r = a.reward[s];
+                max_abs_r = fmax(max_abs_r, fabs(r));
+                const double er = exp(r);                                   // np.exp(reward)   :142
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const int succ = a.idx[(size_t)j * S + s];
+                    double q = 0.0;
+#pragma unroll
+                    for (int aa = 0; aa < A; ++aa) q += __ldg(a.p + ((size_t)aa * K + j) * S + s);
+                    q *= er;
+                    const int off = succ - s;
+                    w[c][0] += (off == -n) ? q : 0.0;
+                    w[c][1] += (off == -1) ? q : 0.0;
+                    w[c][2] += (off == 0) ? q : 0.0;
+                    w[c][3] += (off == 1) ? q : 0.0;
+                    w[c][4] += (off == n) ? q : 0.0;
+                }
+                z0 = a.term[s] ? 1.0 : 0.0;                                 // zs[terminal] = 1.0  :146-147
+            }
+            cur[c] = z0;
+            *reinterpret_cast<double *>(smem_raw + own + 8 * c) = z0;
+            *reinterpret_cast<double *>(smem_raw + own + 8 * c + STRIDE) = 0.0;
+        }
+    const int R = backward_rescale_period(block_max(max_abs_r, scratch), A);
+    __syncthreads();
+
+    // ---- n_sweeps - 1 merged-weight sweeps -------------------------------------------------
+    const int n_lin = a.n_sweeps - 1;
+    for (int t = 0; t < n_lin; ++t) {
+        const double m = (t & 1)
+            ? lin_grid5_sweep<TY, TX, MAXT, STRIDE, 0>(smem_raw, own, nb_up, nb_dn, nb_lf, nb_rt, w, cur)
+            : lin_grid5_sweep<TY, TX, MAXT, 0, STRIDE>(smem_raw, own, nb_up, nb_dn, nb_lf, nb_rt, w, cur);
+        if ((t + 1) % R == 0 && t + 1 < n_lin) {
+            const double gm = block_max(m, scratch);           // two barriers inside
+            if (gm > 0.0 && gm < INFINITY) {
+                const int e = frexp_exponent(gm);
+                const uint32_t offw = (t & 1) ? 0u : (uint32_t)STRIDE;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    cur[c] = ldexp(cur[c], -e);
+                    *reinterpret_cast<double *>(smem_raw + own + 8 * c + offw) = cur[c];
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- last sweep, exactly as the reference evaluates it -----------------------------------
+    if (live) {
+#pragma unroll
+        for (int iy = 0; iy < TY; ++iy)
+#pragma unroll
+            for (int ix = 0; ix < TX; ++ix) lin[(ty * TY + iy) * n + tx * TX + ix] = cur[iy * TX + ix];
+    }
+    __syncthreads();
+    if (live && a.n_sweeps > 0) {
+#pragma unroll 1
+        for (int c = 0; c < C; ++c) {
+            const int s = (ty * TY + c / TX) * n + tx * TX + c % TX;
+            const double er = exp(a.reward[s]);
+            double za[A];
+            const double zs = succ_update<kOpBackward, 4>(
+                A, K, [&](int aa, int j) { return __ldg(a.p + ((size_t)aa * K + j) * S + s); },
+                [&](int j) { return lin[__ldg(a.idx + (size_t)j * S + s)]; }, er, 0.0, 0.0, 0, za);
+#pragma unroll
+            for (int aa = 0; aa < A; ++aa) a.policy[(size_t)s * A + aa] = za[aa] / zs;      // :159
+        }
+    }
+}
+
+template <int TY, int TX, int MAXT, int MINB>
+static int launch_backward_grid5(const SuccBatch &bt, int B, int n, cudaStream_t st);
+
 template <class Kern> static int prep_smem(Kern k, size_t bytes);
 static inline int round_up32(int x);
 template <int TY, int TX, int MAXT, int MINB>
@@ -498,6 +658,16 @@ static int env_int(const char *name, int dflt) {
 // fast path = the table shape of every 4-action grid world
 static inline bool is_fast_shape(int A, int K) { return A == 4 && K == 5; }
 
+template <int TY, int TX, int MAXT, int MINB>
+static int launch_backward_grid5(const SuccBatch &bt, int B, int n, cudaStream_t st) {
+    using Cfg = Grid5Cfg<TY, TX, MAXT>;
+    auto k = backward_grid5_kernel<TY, TX, MAXT, MINB>;
+    const size_t sm = 2 * (size_t)Cfg::STRIDE + 256 + sizeof(double) * (size_t)n * n;
+    if (int rc = prep_smem(k, sm)) return rc;
+    k<<<B, round_up32((n / TX) * (n / TY)), sm, st>>>(bt, n);
+    return IRLB200_OK;
+}
+
 // ---- CTA: successor phases --------------------------------------------------
 template <int OP>
 static int launch_succ_cta(const SuccBatch &bt, int B, cudaStream_t st) {
@@ -505,6 +675,18 @@ static int launch_succ_cta(const SuccBatch &bt, int B, cudaStream_t st) {
     const size_t smem = cta_smem_bytes(S, A, false);
     const bool fast = is_fast_shape(A, K);
     const int force_stream = env_int("IRLB200_FORCE_STREAMED", 0);
+    const int gn = bt.a.grid_n;
+    if (OP == kOpBackward && fast && !force_stream && gn > 0 && gn * gn == S && gn % 4 == 0 &&
+        env_int("IRLB200_BWD_TILE", 1) && bt.a.n_sweeps > 0) {
+        int rc = -100;
+        if ((gn / 4) * (gn / 2) <= 128) rc = launch_backward_grid5<2, 4, 128, 3>(bt, B, gn, st);
+        else if ((gn / 4) * (gn / 2) <= 512) rc = launch_backward_grid5<2, 4, 512, 1>(bt, B, gn, st);
+        if (rc != -100) {
+            if (rc) return rc;
+            LAUNCH_CHECK("backward_grid5_kernel");
+            return IRLB200_OK;
+        }
+    }
     if (fast && S <= 512 && !force_stream) {
         auto k = succ_cta_kernel<OP, 4, 5, 1, 512, 1>;
         if (int rc = prep_smem(k, smem)) return rc;
@@ -776,6 +958,7 @@ static void fill_succ(SuccArgs &a, const irlb200_tables *t) {
     a = SuccArgs{};
     a.S = t->S; a.A = t->A; a.K = t->Ks;
     a.idx = t->succ_idx; a.p = t->succ_p;
+    a.grid_n = t->stencil_n;
 }
 
 static void succ_strides(SuccBatch &bt, const irlb200_tables *t) {

@@ -369,7 +369,9 @@ def test_irl_other_optimizers_and_dense_features(golden):
 # -------------------------------------------------- batched + larger sizes ---
 
 def test_batch_equals_loop():
-    """B independent worlds in one launch == B single launches (bitwise)."""
+    """B independent worlds in one launch == B single launches of the same kernels (bitwise);
+    fused and split launches agree to rounding (the split path uses the merged-weight backward
+    sweeps, the fused one the per-action form)."""
     n, B = 12, 7
     S = n * n
     ps = 0.1 + 0.2 * np.arange(B) / B
@@ -383,8 +385,12 @@ def test_batch_equals_loop():
             nb = E.last_info.counts()
             for b in range(B):
                 d1, _ = M.compute_expected_svf_batch(tabs.select(b), p0, [S - 1], rewards[b], causal=causal,
-                                                     discount=0.9, fused=True)
+                                                     discount=0.9, fused=fused)
                 assert (d[b] == d1[0]).all()
+                assert (nb[b] == E.last_info.counts()[0]).all()
+                d2, _ = M.compute_expected_svf_batch(tabs.select(b), p0, [S - 1], rewards[b], causal=causal,
+                                                     discount=0.9, fused=not fused)
+                close(d[b], d2[0].cpu().numpy(), rtol=1e-11)
                 assert (nb[b] == E.last_info.counts()[0]).all()
     # one of them against the oracle
     mdp = SP.icy_gridworld_sparse(n, ps[3])
