@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--max-sweeps", type=int, default=2000000,
                     help="guard per fixed point (the reference has none); worlds that hit it are reported")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the C1/C2/C3 side measurements")
     ap.add_argument("--cpu-budget", type=float, default=240.0, help="seconds for the whole reference arm")
     return ap.parse_args()
 
@@ -227,6 +228,115 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------
+# side measurements of the other BASELINE configs (not the headline; N = 1 only)
+# ---------------------------------------------------------------------------
+
+def other_configs():
+    """C1 / C2: the seeded 5x5 `irl` / `irl_causal` runs of main.py end to end through the public API
+    (fixture trajectories, numpy in / numpy out); C3: one causal gradient-step body of a single 128x128
+    world in cooperative-grid mode.  Wall-clock with a synchronize on both sides."""
+    import torch
+    import _irlb200 as E
+    import gridworld as W
+    import maxent as M
+    import optimizer as O
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_oracle_golden import load_trajectories
+    out = {}
+    g = np.load(os.path.join(ROOT, "tests", "golden", "e2e_5x5.npz"))
+    world, tjs = W.IcyGridWorld(5, 0.2), load_trajectories(g)
+    F = W.state_features(world)
+
+    class Count:
+        def __init__(self, inner):
+            self.inner, self.n = inner, 0
+
+        def reset(self, p):
+            self.inner.reset(p)
+
+        def step(self, grad):
+            self.n += 1
+            return self.inner.step(grad)
+
+    runs = (("C1_irl_5x5", lambda o: M.irl(world.p_transition, F, [24], tjs, o, O.Constant(1.0)), "irl_steps"),
+            ("C2_irl_causal_5x5_g0.9",
+             lambda o: M.irl_causal(world.p_transition, F, [24], tjs, o, O.Constant(1.0), 0.9), "irl_causal_0.9_steps"))
+    for name, fn, key in runs:
+        best = None
+        for _ in range(3):
+            o = Count(O.ExpSga(lr=O.linear_decay(lr0=0.2)))
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            fn(o)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t
+            best = dt if best is None else min(best, dt)
+        out[name] = {"outer_steps": o.n, "reference_outer_steps": int(g[key]), "seconds": best,
+                     "grad_steps_per_s": o.n / best}
+    n = 128
+    S = n * n
+    tabs = E.gridworld_tables(n, 0.2)
+    p0 = np.zeros(S); p0[0] = 1.0
+    r = np.full(S, -0.1); r[S - 1] = 1.0
+    mask, phi = E.terminal_mask([S - 1], S), E.terminal_phi([S - 1], S)
+    rd, p0d = E.to_device(r), E.to_device(p0)
+    best = None
+    for _ in range(2):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        pol = E.soft_vi(tabs, phi, rd, 0.9, mode=E.MODE_GRID)
+        n_lap = E.last_info.n_iter
+        d = E.svf(tabs, p0d, mask, pol, 1e-5, mode=E.MODE_GRID)
+        n_svf = E.last_info.n_iter
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    n_lap, n_svf = int(n_lap.item()), int(n_svf.item())
+    out["C3_causal_step_128x128"] = {
+        "soft_vi_sweeps": n_lap, "svf_sweeps": n_svf, "seconds": best, "grad_steps_per_s": 1.0 / best,
+        "us_per_sweep": 1e6 * best / (n_lap + n_svf),
+        "algorithmic_GBps": (n_lap * BWD_BYTES_PER_STATE_SWEEP + n_svf * SVF_BYTES_PER_STATE_SWEEP) * S / best / 1e9,
+        "note": "sync-latency bound: 3.5 MB of tables are register/L2 resident, one grid barrier per sweep"}
+    out["roofline_stream"] = stream_roofline()
+    return out
+
+
+def stream_roofline(n=2048, fw_sweeps=400, lap_sweeps=150):
+    """The physically HBM-bound regime (BASELINE configs[4] on ONE GPU): a single 2048x2048 world
+    (4.2 M states, 1.5 GB of tables >> 126 MB L2) in cooperative-grid mode with streamed table rows,
+    fixed sweep budgets.  achieved = algorithmic bytes / CUDA-event time of the launch."""
+    import torch
+    import _irlb200 as E
+    S = n * n
+    tabs = E.gridworld_tables(n, 0.2)
+    dev = tabs.succ_idx.device
+    p0 = torch.zeros(S, dtype=torch.float64, device=dev); p0[0] = 1.0
+    r = torch.full((S,), -0.1, dtype=torch.float64, device=dev); r[S - 1] = 1.0
+    mask = torch.zeros(S, dtype=torch.uint8, device=dev); mask[S - 1] = 1
+    phi = torch.full((S,), -float("inf"), dtype=torch.float64, device=dev); phi[S - 1] = 0.0
+    peak = 6650.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    res = {"workload": "single %dx%d IcyGridWorld, streamed cooperative-grid kernels, fixed sweep budgets" % (n, n),
+           "states": S, "table_bytes": tabs.nbytes(), "peak": peak, "unit": "GB/s"}
+    for rep in range(2):                                   # first pass warms up (workspace allocation)
+        E.launch_log = []
+        pol = E.soft_vi(tabs, phi, r, 0.9, max_sweeps=lap_sweeps, mode=E.MODE_GRID)
+        d = E.svf(tabs, p0, mask, pol, 1e-5, max_sweeps=fw_sweeps, mode=E.MODE_GRID)
+        torch.cuda.synchronize()
+        log, E.launch_log = E.launch_log, None
+    ms = {name: a.elapsed_time(b) for name, a, b in log}
+    for key, name, sweeps, bps in (("forward", "svf", fw_sweeps, SVF_BYTES_PER_STATE_SWEEP),
+                                   ("soft_vi", "soft_vi", lap_sweeps, BWD_BYTES_PER_STATE_SWEEP)):
+        ach = bps * S * sweeps / (ms[name] / 1e3) / 1e9
+        res[key] = {"sweeps": sweeps, "launch_ms": ms[name], "us_per_sweep": 1e3 * ms[name] / sweeps,
+                    "bytes_per_state_sweep": bps, "achieved": ach, "frac": ach / peak}
+    return res
+
+
+# ---------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------
 
@@ -364,6 +474,11 @@ def run_b200_arm(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * S * 8,
                         "d2h_bytes_per_step": B * S * 8},
                 "gpu_launches": int(launches), "roofline": roofline}
+        if world == 1 and not args.no_other_configs:
+            try:
+                line["other_configs"] = other_configs()
+            except Exception as e:                                         # side measurements never sink the line
+                line["other_configs"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             t, n_svf = cpu_full_body(w, 0)
             line["cpu_baseline"] = {"value": 1.0 / t, "unit": UNIT, "cores": blas_threads(), "kind": "port",

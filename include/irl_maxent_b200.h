@@ -50,6 +50,7 @@ extern "C" {
 #define IRLB200_ST_CONVERGED   0   /* stopped because delta <= eps (or fixed count reached) */
 #define IRLB200_ST_NONFINITE   1   /* stopped because delta was NaN (reference: NaN ends the loop) */
 #define IRLB200_ST_MAXSWEEPS   2   /* stopped by the max_sweeps guard (reference would keep looping) */
+#define IRLB200_ST_ABORTED     3   /* slab mode: a peer rank did not show up within the timeout */
 
 /* execution modes for a single problem (batched calls always use IRLB200_MODE_CTA) */
 #define IRLB200_MODE_AUTO     0
@@ -207,6 +208,36 @@ int irlb200_slab_sweep(int op, int lo, int cnt, int A, int K, const int32_t *idx
  * terminal_mask [S_total] are globally indexed (ghost rows exchanged by the caller). */
 int irlb200_slab_weights(int cnt, int A, int K, const int32_t *pred_idx, const double *pred_p,
                          const double *policy, const uint8_t *terminal_mask, double *W, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * slab mode with the halo exchange inside the kernel (NVLink peer stores, no collective call).
+ * Every rank owns a block of irlb200_slab_block_bytes(S_total) bytes from irlb200_peer_alloc
+ * ([1 KiB barrier/flag header | iterate buffer 0 [S_total] | iterate buffer 1 [S_total]]),
+ * exports it with irlb200_ipc_export (64-byte CUDA IPC handle, exchanged by the host layer over
+ * torch.distributed) and maps the others with irlb200_ipc_import.  The header must be zero on all
+ * ranks before any rank launches.  irlb200_slab_persistent runs one whole fixed point of the
+ * slab [lo, lo+cnt) in ONE cooperative launch per rank:
+ *   op 1 soft-VI  (idx/p successor rows [K][cnt] / [A][K][cnt], c0 reward, c1 phi; policy_out [cnt][A],
+ *                  out = value [cnt])
+ *   op 2 value iteration (c0 reward; out = value [cnt])
+ *   op 3 forward pass (idx/p predecessor rows, c0 p_initial; policy_in [S_total][A] and
+ *                  terminal_mask [S_total] globally indexed with valid ghost rows; w_scratch [K][cnt];
+ *                  out = svf [cnt])
+ * halo = ghost width in states (one grid row).  blocks[r] = base of rank r's block (world <= 16).
+ * ------------------------------------------------------------------------- */
+int    irlb200_peer_alloc(size_t bytes, void **ptr);
+int    irlb200_peer_free(void *ptr);
+int    irlb200_ipc_export(void *ptr, unsigned char *handle64);
+int    irlb200_ipc_import(const unsigned char *handle64, void **ptr);
+int    irlb200_ipc_close(void *ptr);
+size_t irlb200_slab_block_bytes(int S_total);
+int    irlb200_slab_reset(void *block, void *stream);      /* zero the header (all ranks, before a launch) */
+int    irlb200_slab_persistent(int op, int rank, int world, void *const *blocks, int S_total, int lo,
+                               int cnt, int halo, int A, int K, const int32_t *idx, const double *p,
+                               const double *c0, const double *c1, const double *policy_in,
+                               const uint8_t *terminal_mask, double *w_scratch, double discount,
+                               double eps, int max_sweeps, int vi_mean, double *out, double *policy_out,
+                               int32_t *n_iter, int32_t *status, double timeout_s, void *stream);
 
 /* ------------------------------------------------------------------------- *
  * dense feature products on the path: reward = features . theta (maxent.py:244)

@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libirlmaxent_b200.so")
 
 MODE_AUTO, MODE_CTA, MODE_CLUSTER, MODE_GRID = 0, 1, 2, 3
-ST_CONVERGED, ST_NONFINITE, ST_MAXSWEEPS = 0, 1, 2
+ST_CONVERGED, ST_NONFINITE, ST_MAXSWEEPS, ST_ABORTED = 0, 1, 2, 3
 
 # guard against inputs for which the reference would loop forever
 # (non-absorbing policies, maxent.py:108); 0 disables the guard
@@ -56,6 +56,15 @@ SIGNATURES = {
     "irlb200_gridworld_tables_range": ([_i, _i, _d, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "irlb200_slab_sweep": ([_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _d, _d, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "irlb200_slab_weights": ([_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "irlb200_peer_alloc": ([ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)], _i),
+    "irlb200_peer_free": ([_vp], _i),
+    "irlb200_ipc_export": ([_vp, ctypes.c_char_p], _i),
+    "irlb200_ipc_import": ([ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)], _i),
+    "irlb200_ipc_close": ([_vp], _i),
+    "irlb200_slab_block_bytes": ([_i], ctypes.c_size_t),
+    "irlb200_slab_reset": ([_vp, _vp], _i),
+    "irlb200_slab_persistent": ([_i, _i, _i, ctypes.POINTER(ctypes.c_void_p), _i, _i, _i, _i, _i, _i, _vp, _vp, _vp,
+                                 _vp, _vp, _vp, _vp, _d, _d, _i, _i, _vp, _vp, _vp, _vp, _d, _vp], _i),
     "irlb200_backward": ([_tp, _i, _vp, _vp, _i, _i, _vp, _i, _vp], _i),
     "irlb200_soft_vi": ([_tp, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _i, _vp], _i),
     "irlb200_value_iteration": ([_tp, _i, _vp, _d, _d, _i, _i, _vp, _vp, _vp, _i, _vp], _i),

@@ -40,6 +40,9 @@ struct SuccArgs {
     int max_sweeps;              // <= 0: unguarded
     int vi_mean;                 // VI: 1 = average over actions (solver.py:100)
     int grid_n;                  // > 0: successor offsets lie in {-n,-1,0,+1,+n} (grid stencil)
+    int s_off;                   // streamed flavour: iterate index of local state 0 (slab mode; else 0).
+                                 // Tables / per-state vectors are local (length S), neighbour indices and
+                                 // the iterate are global.
     double *policy;              // [S][A] out (generic address: shared or global) or null
     double *policy2;             // optional second copy (global) or null
     double *value;               // [S] out (global) or null
@@ -54,6 +57,8 @@ struct SvfArgs {
     const double *policy;        // [S][A] (generic address)
     double *w_scratch;           // [K][S] global scratch, streamed flavour only
     int grid_n;                  // > 0: predecessor offsets lie in {-n,-1,0,+1,+n} (grid stencil), n = grid_n
+    int s_off;                   // streamed flavour: iterate index of local state 0 (slab mode; else 0);
+                                 // policy / term are then indexed globally
     double eps;
     int max_sweeps;
     double *svf;                 // [S] out
@@ -171,7 +176,7 @@ __device__ void succ_phase(Topo &tp, const SuccArgs &a, int *n_iter_out, int *st
     } else {
         for (int s = r0; s < S; s += NT) {
             max_abs_r = fmax(max_abs_r, fabs(a.reward[s]));
-            tp.store(0, s, succ_init_value<OP>(OP == kOpBackward && a.term[s]));
+            tp.store(0, a.s_off + s, succ_init_value<OP>(OP == kOpBackward && a.term[s]));
         }
     }
     int R = 0;
@@ -214,9 +219,9 @@ __device__ void succ_phase(Topo &tp, const SuccArgs &a, int *n_iter_out, int *st
                         A, K, [&](int aa, int j) { return __ldg(a.p + ((size_t)aa * K + j) * S + s); },
                         [&](int j) { return tp.load(b, __ldg(a.idx + (size_t)j * S + s)); }, k0, k1,
                         a.discount, a.vi_mean, nullptr);
-                    if (!fixed) v.add(x, tp.load(b, s), a.eps);
+                    if (!fixed) v.add(x, tp.load(b, a.s_off + s), a.eps);
                     local_max = fmax(local_max, x);
-                    tp.store(b ^ 1, s, x);
+                    tp.store(b ^ 1, a.s_off + s, x);
                 }
             }
             ++n;
@@ -235,7 +240,7 @@ __device__ void succ_phase(Topo &tp, const SuccArgs &a, int *n_iter_out, int *st
                             }
                         } else {
                             for (int s = r0; s < S; s += NT)
-                                tp.store(b ^ 1, s, ldexp(tp.load(b ^ 1, s), -e));
+                                tp.store(b ^ 1, a.s_off + s, ldexp(tp.load(b ^ 1, a.s_off + s), -e));
                         }
                     }
                 }
@@ -293,7 +298,7 @@ __device__ void succ_phase(Topo &tp, const SuccArgs &a, int *n_iter_out, int *st
     }
     if (a.value) {
         const int b = n & 1;
-        for (int s = r0; s < S; s += NT) a.value[s] = tp.load(b, s);
+        for (int s = r0; s < S; s += NT) a.value[s] = tp.load(b, (REG ? 0 : a.s_off) + s);
     }
     if (r0 == 0) {
         if (n_iter_out) *n_iter_out = n;
@@ -350,7 +355,7 @@ __device__ void svf_phase(Topo &tp, const SvfArgs &a, int *n_iter_out, int *stat
         for (int s = r0; s < S; s += NT) {
             for (int j = 0; j < K; ++j)
                 a.w_scratch[(size_t)j * S + s] = weight(s, j, a.idx[(size_t)j * S + s]);
-            tp.store(0, s, 0.0);
+            tp.store(0, a.s_off + s, 0.0);
         }
     }
     tp.sync();
@@ -380,8 +385,8 @@ __device__ void svf_phase(Topo &tp, const SvfArgs &a, int *n_iter_out, int *stat
                 for (int j = 0; j < K; ++j)
                     acc = fma(a.w_scratch[(size_t)j * S + s], tp.load(b, __ldg(a.idx + (size_t)j * S + s)), acc);
                 const double x = __ldg(a.p0 + s) + acc;
-                v.add(x, tp.load(b, s), a.eps);
-                tp.store(b ^ 1, s, x);
+                v.add(x, tp.load(b, a.s_off + s), a.eps);
+                tp.store(b ^ 1, a.s_off + s, x);
             }
         }
         ++n;
@@ -392,7 +397,7 @@ __device__ void svf_phase(Topo &tp, const SvfArgs &a, int *n_iter_out, int *stat
 
     const int b = n & 1;
     for (int s = r0; s < S; s += NT) {
-        const double d = tp.load(b, s);
+        const double d = tp.load(b, (REG ? 0 : a.s_off) + s);
         a.svf[s] = d;
         if (a.grad) a.grad[s] = a.e_features[s] - d;                    // maxent.py:248, features = I
     }

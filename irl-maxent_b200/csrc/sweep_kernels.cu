@@ -287,10 +287,11 @@ struct Grid5Cfg {
 };
 
 template <int TY, int TX, int MAXT, int OFF_R, int OFF_W>
-__device__ __forceinline__ bool svf_grid5_sweep(unsigned char *smem, uint32_t own, uint32_t nb_up, uint32_t nb_dn,
+__device__ __forceinline__ void svf_grid5_sweep(unsigned char *smem, uint32_t own, uint32_t nb_up, uint32_t nb_dn,
                                                 uint32_t nb_lf, uint32_t nb_rt, const double (&w)[TY * TX][5],
-                                                const double (&p0r)[TY * TX], double (&cur)[TY * TX], double eps) {
-    double up[TX], dn[TX], lf[TY], rt[TY], x[TY * TX];
+                                                const double (&p0r)[TY * TX], const double (&cur)[TY * TX],
+                                                double (&x)[TY * TX]) {
+    double up[TX], dn[TX], lf[TY], rt[TY];
 #pragma unroll
     for (int ix = 0; ix < TX; ++ix) {
         up[ix] = *reinterpret_cast<const double *>(smem + nb_up + 8 * ((TY - 1) * TX + ix) + OFF_R);
@@ -317,14 +318,8 @@ __device__ __forceinline__ bool svf_grid5_sweep(unsigned char *smem, uint32_t ow
             acc = fma(w[c][4], v_dn, acc);
             x[c] = p0r[c] + acc;                                        // p_initial + sum   maxent.py:110
         }
-    bool go = false;
 #pragma unroll
-    for (int c = 0; c < TY * TX; ++c) {
-        *reinterpret_cast<double *>(smem + own + 8 * c + OFF_W) = x[c];
-        go |= !(fabs(x[c] - cur[c]) <= eps);                            // |diff| > eps, or NaN
-        cur[c] = x[c];
-    }
-    return go;
+    for (int c = 0; c < TY * TX; ++c) *reinterpret_cast<double *>(smem + own + 8 * c + OFF_W) = x[c];
 }
 
 template <int TY, int TX, int MAXT, int MINB>
@@ -383,15 +378,28 @@ __global__ void __launch_bounds__(MAXT, MINB) svf_grid5_kernel(const SvfBatch bt
     if (tid == 0) *flag = 0;
     __syncthreads();
 
+    // Stop rule (`while delta > eps`, maxent.py:108-112), exact but cheap: a sweep must continue as
+    // soon as ANY state moved by more than eps, so each thread first votes with one cell of its tile
+    // only; the full per-cell test (and a second bar.red) runs just in the sweeps where that sampled
+    // vote finds nothing -- the last few hundred of ~10^4..10^5.  Stopping always needs the full test.
     const double eps = a.eps;
     const int limit = a.max_sweeps > 0 ? a.max_sweeps : 0x7fffffff;
     int nsw = 0, status = IRLB200_ST_CONVERGED;
     for (;;) {
-        const bool go = (nsw & 1)
-            ? svf_grid5_sweep<TY, TX, MAXT, STRIDE, 0>(smem_raw, own, nb_up, nb_dn, nb_lf, nb_rt, w, p0r, cur, eps)
-            : svf_grid5_sweep<TY, TX, MAXT, 0, STRIDE>(smem_raw, own, nb_up, nb_dn, nb_lf, nb_rt, w, p0r, cur, eps);
+        double x[C];
+        if (nsw & 1) svf_grid5_sweep<TY, TX, MAXT, STRIDE, 0>(smem_raw, own, nb_up, nb_dn, nb_lf, nb_rt, w, p0r, cur, x);
+        else svf_grid5_sweep<TY, TX, MAXT, 0, STRIDE>(smem_raw, own, nb_up, nb_dn, nb_lf, nb_rt, w, p0r, cur, x);
         ++nsw;
-        if (!__syncthreads_or(go ? 1 : 0)) break;
+        bool stop = false;
+        if (!__syncthreads_or(!(fabs(x[0] - cur[0]) <= eps) ? 1 : 0)) {
+            bool go = false;
+#pragma unroll
+            for (int c = 1; c < C; ++c) go |= !(fabs(x[c] - cur[c]) <= eps);   // |diff| > eps, or NaN
+            stop = !__syncthreads_or(go ? 1 : 0);
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) cur[c] = x[c];
+        if (stop) break;                                                // delta <= eps: converged
         if ((nsw & 15) == 0) {
             bool bad = false;
 #pragma unroll

@@ -23,7 +23,7 @@ a numpy sweep there); the product backend below is CUDA-only, no CPU fallback.
 
 import numpy as np
 
-ST_CONVERGED, ST_NONFINITE, ST_MAXSWEEPS = 0, 1, 2
+ST_CONVERGED, ST_NONFINITE, ST_MAXSWEEPS, ST_ABORTED = 0, 1, 2, 3
 OP_SOFT_VI, OP_VI, OP_SVF = 1, 2, 3
 NEG_HUGE = -1e200           # reference: maxent.py:323
 
@@ -240,3 +240,107 @@ class SlabGrid:
         parts = [torch.empty_like(mine) for _ in sizes]
         dist.all_gather(parts, mine, group=self.group)
         return torch.cat([p[:s] for p, s in zip(parts, sizes)], 0)
+
+
+class PeerSlabGrid(SlabGrid):
+    """Slab mode with the halo exchange inside the kernel: one persistent cooperative launch per
+    rank and fixed point (`irlb200_slab_persistent`), boundary rows pushed into the neighbours'
+    ghost rows with NVLink peer stores, stop rule all-reduced through peer-mapped flag words.
+    torch.distributed is used for plumbing only: exchanging the CUDA IPC handles once, one
+    ghost-row exchange of the policy before the forward pass, and a process-group barrier
+    around each launch.  CUDA only."""
+
+    def __init__(self, size, p_slip=0.2, icy=True, group=None, timeout_s=20.0):
+        super().__init__(size, p_slip, icy, group=group, backend=CudaBackend())
+        import ctypes
+        E = self.backend.E
+        self.E, self.ct = E, ctypes
+        self.timeout_s = float(timeout_s)
+        nbytes = E._lib.irlb200_slab_block_bytes(self.n_states)
+        own = ctypes.c_void_p()
+        E._check(E._lib.irlb200_peer_alloc(nbytes, ctypes.byref(own)))
+        self._own, self._nbytes = own, nbytes
+        self._imported = []
+        ptrs = [None] * self.world
+        ptrs[self.rank] = own.value
+        if self.world > 1:
+            handle = ctypes.create_string_buffer(64)
+            E._check(E._lib.irlb200_ipc_export(own, handle))
+            gathered = [None] * self.world
+            self.dist.all_gather_object(gathered, bytes(handle.raw), group=self.group)
+            for r, h in enumerate(gathered):
+                if r == self.rank:
+                    continue
+                p = ctypes.c_void_p()
+                E._check(E._lib.irlb200_ipc_import(ctypes.create_string_buffer(h, 64), ctypes.byref(p)))
+                ptrs[r] = p.value
+                self._imported.append(p)
+        self._blocks = (ctypes.c_void_p * self.world)(*ptrs)
+
+    def close(self):
+        E = self.E
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+        for p in self._imported:
+            E._lib.irlb200_ipc_close(p)
+        self._imported = []
+        if self._own is not None:
+            E._lib.irlb200_peer_free(self._own)
+            self._own = None
+
+    def _fence(self):
+        """All ranks idle and every header zero before anybody launches."""
+        torch, E = self.torch, self.E
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+        E._check(E._lib.irlb200_slab_reset(self._own, E._stream()))
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+
+    def _run(self, op, idx, p, c0, c1, policy_in, mask, w_scratch, discount, eps, max_sweeps, vi_mean, policy_out):
+        torch, E = self.torch, self.E
+        out = torch.empty(self.cnt, dtype=torch.float64, device=self.device)
+        n_iter = torch.zeros(1, dtype=torch.int32, device=self.device)
+        status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._fence()
+        ms = E.DEFAULT_MAX_SWEEPS if max_sweeps is None else int(max_sweeps)
+        with E._timed("slab_persistent"):
+            E._check(E._lib.irlb200_slab_persistent(
+                op, self.rank, self.world, self._blocks, self.n_states, self.lo, self.cnt, self.halo, self.A, self.K,
+                E._ptr(idx), E._ptr(p), E._ptr(c0), E._ptr(c1), E._ptr(policy_in), E._ptr(mask), E._ptr(w_scratch),
+                float(discount), float(eps), ms, int(vi_mean), E._ptr(out), E._ptr(policy_out), E._ptr(n_iter),
+                E._ptr(status), self.timeout_s, E._stream()))
+        torch.cuda.synchronize()
+        self.last_n_iter, self.last_status = int(n_iter.item()), int(status.item())
+        if self.last_status == ST_ABORTED:
+            raise RuntimeError("slab kernel aborted: a peer rank did not arrive within %.0f s" % self.timeout_s)
+        return out
+
+    def soft_vi(self, reward_local, phi_local, discount, eps=1e-5, max_sweeps=None):
+        torch, t = self.torch, self.tables
+        r, phi = self._dev(reward_local), self._dev(phi_local)
+        pol = torch.empty((self.cnt, self.A), dtype=torch.float64, device=self.device)
+        v = self._run(OP_SOFT_VI, t["succ_idx"], t["succ_p"], r, phi, None, None, None, discount, eps, max_sweeps, 0, pol)
+        return pol, v
+
+    def value_iteration(self, reward_local, discount, eps=1e-3, max_sweeps=None, mean=False):
+        t = self.tables
+        r = self._dev(reward_local)
+        return self._run(OP_VI, t["succ_idx"], t["succ_p"], r, None, None, None, None, discount, eps, max_sweeps,
+                         1 if mean else 0, None)
+
+    def svf(self, p_initial_local, terminal, policy_local, eps=1e-5, max_sweeps=None):
+        torch, t = self.torch, self.tables
+        S = self.n_states
+        pol_full = torch.zeros((S, self.A), dtype=torch.float64, device=self.device)
+        pol_full[self.lo:self.hi] = self._dev(policy_local)
+        self.exchange(pol_full, width=self.A)                 # ghost rows of the policy, once per pass
+        mask = np.zeros(S, dtype=np.uint8)
+        mask[np.asarray(list(terminal), dtype=np.int64)] = 1
+        mask_d = torch.as_tensor(mask).to(self.device)
+        W = torch.empty((self.K, self.cnt), dtype=torch.float64, device=self.device)
+        p0 = self._dev(p_initial_local)
+        return self._run(OP_SVF, t["pred_idx"], t["pred_p"], p0, None, pol_full, mask_d, W, 0.0, eps, max_sweeps, 0, None)

@@ -493,3 +493,36 @@ def test_slab_single_rank_matches_engine_and_oracle():
     val = g.value_iteration(r, 0.95, 1e-5)
     assert g.last_n_iter == n_vi
     close(val, vref)
+
+
+def test_peer_slab_single_rank():
+    """The persistent slab kernel (in-kernel barrier / vote path) with one rank: same results and
+    sweep counts as the oracle and bitwise the same as the single-GPU engine."""
+    import slab
+    n = 16
+    S = n * n
+    g = slab.PeerSlabGrid(n, 0.2, icy=True)
+    try:
+        r = np.full(S, -0.1); r[S - 1] = 1.0
+        phi = np.full(S, -np.inf); phi[S - 1] = 0.0
+        p0 = np.zeros(S); p0[0] = 1.0
+        mdp = SP.icy_gridworld_sparse(n, 0.2)
+        pa, n_lap = SP.local_causal_action_probabilities(mdp, [S - 1], r, 0.9)
+        dref, n_svf = SP.expected_svf_from_policy(mdp, p0, [S - 1], pa)
+        pol, v = g.soft_vi(r, phi, 0.9, 1e-5)
+        assert g.last_n_iter == n_lap and g.last_status == 0
+        close(pol, pa)
+        d = g.svf(p0, [S - 1], pol, 1e-5)
+        assert g.last_n_iter == n_svf
+        close(d, dref)
+        t = E.gridworld_tables(n, 0.2)
+        pol_e = E.soft_vi(t, E.terminal_phi([S - 1], S), r, 0.9)
+        assert (pol_e[0] == pol).all()
+        vref, n_vi = SP.value_iteration(mdp, r, 0.95, 1e-5)
+        val = g.value_iteration(r, 0.95, 1e-5)
+        assert g.last_n_iter == n_vi
+        close(val, vref)
+        d = g.svf(p0, [S - 1], pol, 1e-5, max_sweeps=25)
+        assert g.last_n_iter == 25 and g.last_status == E.ST_MAXSWEEPS
+    finally:
+        g.close()
