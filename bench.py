@@ -421,18 +421,26 @@ def run_b200_arm(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = svf_bytes / (svf_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "svf_cta_kernel (forward state-visitation sweeps)",
+    # physical DRAM traffic of the same kernel: ncu --set full capture of this command line with
+    # --batch 444 (profiles/r01_svf_grid5_kernel.txt): 103.7 MB read + 5.5 MB written per launch of 444
+    # worlds = 246 kB per world (tables + policy in, svf/grad out, once per fixed point), scaled to B worlds
+    traffic = 246.0e3 * B if S == 1024 else None
+    roofline = {"bound": "hbm", "kernel": "svf_grid5_kernel (forward state-visitation sweeps, stencil-tiled)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
-                "traffic": None,
+                "traffic": traffic,
+                "binding_resource": "on-chip: shared-memory datapath (ncu 73% of peak wavefronts at 3 worlds/SM), "
+                                    "FP64 pipe 47%, issue slots 47%; DRAM 0.9% busy",
                 "algorithmic_bytes_per_launch": svf_bytes, "launch_ms": svf_ms,
                 "share_of_step": svf_ms * args.steps / ms_total if ms_total else None,
                 "forward_sweeps_per_world_mean": float(n_fw.mean()) / B,
                 "forward_sweeps_per_world_max": int(max(int(s[:, 1].max().item()) for s in sweeps)),
                 "worlds_stopped_by_guard": int(sum(int((s[:, 1] == 2).sum().item()) for s in stati)),
-                "note": "tables and weights are register-resident for the whole fixed point, so the algorithmic "
-                        "bytes of a sweep never reach HBM: frac is an efficiency figure against the HBM roofline a "
-                        "streaming implementation would be bound by, not physical DRAM traffic (see DESIGN.md)",
+                "note": "tables, weights and the iterate are register/shared-memory resident for the whole fixed point "
+                        "(10^4-10^5 sweeps per launch), so the algorithmic bytes of a sweep never reach HBM: frac > 1 is "
+                        "an efficiency figure against the roofline a streaming implementation would hit, `traffic` is the "
+                        "physical DRAM volume; the physically HBM-bound regime is other_configs.roofline_stream "
+                        "(see DESIGN.md section 4)",
                 "backward": {"launch_ms": bwd_ms, "algorithmic_bytes_per_launch": bwd_bytes,
                              "achieved": bwd_bytes / (bwd_ms / 1e3) / 1e9 if bwd_ms == bwd_ms else None}}
 
