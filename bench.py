@@ -234,7 +234,7 @@ def run_reference_arm(args):
 def other_configs():
     """C1 / C2: the seeded 5x5 `irl` / `irl_causal` runs of main.py end to end through the public API
     (fixture trajectories, numpy in / numpy out); C3: one causal gradient-step body of a single 128x128
-    world in cooperative-grid mode.  Wall-clock with a synchronize on both sides."""
+    world; C4 causal: the headline batch with the MaxCausalEnt body.  Wall-clock, synchronize on both sides."""
     import torch
     import _irlb200 as E
     import gridworld as W
@@ -286,7 +286,7 @@ def other_configs():
         t = time.perf_counter()
         pol = E.soft_vi(tabs, phi, rd, 0.9, mode=E.MODE_GRID)
         n_lap = E.last_info.n_iter
-        d = E.svf(tabs, p0d, mask, pol, 1e-5, mode=E.MODE_GRID)
+        d = E.svf(tabs, p0d, mask, pol, 1e-5, mode=E.MODE_AUTO)        # -> thread-block-cluster kernel
         n_svf = E.last_info.n_iter
         torch.cuda.synchronize()
         dt = time.perf_counter() - t
@@ -296,9 +296,36 @@ def other_configs():
         "soft_vi_sweeps": n_lap, "svf_sweeps": n_svf, "seconds": best, "grad_steps_per_s": 1.0 / best,
         "us_per_sweep": 1e6 * best / (n_lap + n_svf),
         "algorithmic_GBps": (n_lap * BWD_BYTES_PER_STATE_SWEEP + n_svf * SVF_BYTES_PER_STATE_SWEEP) * S / best / 1e9,
-        "note": "sync-latency bound: 3.5 MB of tables are register/L2 resident, one grid barrier per sweep"}
+        "note": "sync-latency bound: 3.5 MB of tables are register resident; soft-VI in cooperative-grid mode (one "
+                "grid barrier per sweep), forward pass in thread-block-cluster mode (DSMEM halos, barrier.cluster)"}
+    out["C4_causal_batch"] = causal_batch()
     out["roofline_stream"] = stream_roofline()
     return out
+
+
+def causal_batch(B=4096, n=32):
+    """The headline batch with the MaxCausalEnt gradient-step body (soft-VI gamma = 0.9 to eps 1e-5 +
+    forward pass to eps 1e-5), goal-directed reward -0.1 / +1 at the terminal plus 0.01 N(0,1)."""
+    import torch
+    import _irlb200 as E
+    import maxent as M
+    S = n * n
+    tabs = E.gridworld_tables(n, 0.1 + 0.2 * np.arange(B) / B)
+    r = np.full((B, S), -0.1) + 0.01 * np.random.default_rng(7).standard_normal((B, S))
+    r[:, S - 1] = 1.0
+    p0 = np.zeros(S); p0[0] = 1.0
+    rd = E.to_device(r)
+    best, info = None, None
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        d, _ = M.compute_expected_svf_batch(tabs, p0, [S - 1], rd, causal=True, discount=0.9, fused=False)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t
+        if best is None or dt < best:
+            best, info = dt, E.last_info.counts()
+    return {"worlds": B, "states": S, "seconds": best, "grad_steps_per_s": B / best,
+            "soft_vi_sweeps_mean": float(info[:, 0].mean()), "svf_sweeps_mean": float(info[:, 1].mean())}
 
 
 def stream_roofline(n=2048, fw_sweeps=400, lap_sweeps=150):

@@ -90,9 +90,26 @@ __device__ __forceinline__ double succ_update(int A, int K, PAcc pr, XAcc xv, do
 #pragma unroll
         for (int a = 1; a < An; ++a) x += q[a];                          // za.sum(axis=1)        :156
     } else if (OP == kOpSoftVI) {
-        x = c1;                                                          // v = reward_terminal   :331
+        // v = softmax(...softmax(softmax(phi, q_0), q_1)..., q_{A-1})  (maxent.py:331-333) is
+        // log(e^phi + sum_a e^{q_a}).  The reference folds it pairwise: A dependent exp+log pairs,
+        // ~2 500 cycles of FP64 latency per sweep.  Evaluated here as m + log(sum_i exp(x_i - m)) with
+        // m = max_i x_i: the exps are independent and there is one log (agrees with the fold to a few
+        // ulp; the tests hold policies to 1e-10 and sweep counts exactly).  A non-finite maximum
+        // (+inf, NaN, or everything -inf) takes the reference's fold verbatim.
+        double m = c1;
 #pragma unroll
-        for (int a = 0; a < An; ++a) x = softmax2(x, q[a]);              //                       :332-333
+        for (int a = 0; a < An; ++a) m = max_nan(m, q[a]);
+        if (fabs(m) < INFINITY) {
+            double ssum = 0.0;
+            if (c1 != -INFINITY) ssum = exp(c1 - m);                     // phi = -inf off the terminals
+#pragma unroll
+            for (int a = 0; a < An; ++a) ssum += exp(q[a] - m);
+            x = m + log(ssum);
+        } else {
+            x = c1;                                                      // v = reward_terminal   :331
+#pragma unroll 1
+            for (int a = 0; a < An; ++a) x = softmax2(x, q[a]);          //                       :332-333
+        }
     } else {
         if (vi_mean) {
             x = q[0];

@@ -4,6 +4,8 @@
 //   *_grid_kernel   one problem, cooperative persistent grid (iterate in L2/HBM)
 //   step_cta_kernel fused gradient step: policy phase + forward phase, the
 //                   policy stays in shared memory
+#include <cooperative_groups.h>
+
 #include <cstdio>
 #include <mutex>
 
@@ -429,6 +431,174 @@ __global__ void __launch_bounds__(MAXT, MINB) svf_grid5_kernel(const SvfBatch bt
 }
 
 // ---------------------------------------------------------------------------
+// Cluster variant of the stencil-tiled forward pass: ONE world spread over a thread-block
+// cluster (up to 16 CTAs), for worlds too large for one CTA but small enough that a grid
+// barrier (~1.5 us) would dominate the sweep (BASELINE configs[2], 128 x 128).
+// CTA c of the cluster owns the tile rows [c R, (c+1) R); the up / down halo of its first /
+// last tile row is read straight from the neighbouring CTA's shared memory (DSMEM), the
+// sweep fence is barrier.cluster (arrive.release / wait.acquire), and the stop rule is
+// all-reduced by stamping the sweep number into every CTA's vote word with remote
+// shared-memory stores before the cluster barrier (double-buffered by sweep parity).
+// Same tile arithmetic as svf_grid5_kernel: bitwise identical results.
+// ---------------------------------------------------------------------------
+namespace cgx = cooperative_groups;
+
+template <int TY, int TX, int OFF_R, int OFF_W>
+__device__ __forceinline__ void svf_grid5_cluster_sweep(unsigned char *smem, uint32_t own, const unsigned char *up_p,
+                                                        const unsigned char *dn_p, uint32_t nb_lf, uint32_t nb_rt,
+                                                        const double (&w)[TY * TX][5], const double (&p0r)[TY * TX],
+                                                        const double (&cur)[TY * TX], double (&x)[TY * TX]) {
+    double up[TX], dn[TX], lf[TY], rt[TY];
+#pragma unroll
+    for (int ix = 0; ix < TX; ++ix) {
+        up[ix] = *reinterpret_cast<const double *>(up_p + 8 * ((TY - 1) * TX + ix) + OFF_R);
+        dn[ix] = *reinterpret_cast<const double *>(dn_p + 8 * ix + OFF_R);
+    }
+#pragma unroll
+    for (int iy = 0; iy < TY; ++iy) {
+        lf[iy] = *reinterpret_cast<const double *>(smem + nb_lf + 8 * (iy * TX + TX - 1) + OFF_R);
+        rt[iy] = *reinterpret_cast<const double *>(smem + nb_rt + 8 * (iy * TX) + OFF_R);
+    }
+#pragma unroll
+    for (int iy = 0; iy < TY; ++iy)
+#pragma unroll
+        for (int ix = 0; ix < TX; ++ix) {
+            const int c = iy * TX + ix;
+            const double v_up = iy > 0 ? cur[c - TX] : up[ix];
+            const double v_lf = ix > 0 ? cur[c - 1] : lf[iy];
+            const double v_rt = ix < TX - 1 ? cur[c + 1] : rt[iy];
+            const double v_dn = iy < TY - 1 ? cur[c + TX] : dn[ix];
+            double acc = fma(w[c][0], v_up, 0.0);
+            acc = fma(w[c][1], v_lf, acc);
+            acc = fma(w[c][2], cur[c], acc);
+            acc = fma(w[c][3], v_rt, acc);
+            acc = fma(w[c][4], v_dn, acc);
+            x[c] = p0r[c] + acc;                                        // p_initial + sum   maxent.py:110
+        }
+#pragma unroll
+    for (int c = 0; c < TY * TX; ++c) *reinterpret_cast<double *>(smem + own + 8 * c + OFF_W) = x[c];
+}
+
+// cluster-wide OR of a per-thread predicate: stamp, barrier.cluster, compare.  `word` points at this
+// CTA's vote words [2]; every CTA's copy is written by every voting warp (one lane per target CTA).
+__device__ __forceinline__ bool cluster_any(cgx::cluster_group &cl, int *word, int stamp, bool pred, int ncta) {
+    int *slot = word + (stamp & 1);
+    const unsigned any = __ballot_sync(0xffffffffu, pred);
+    const int lane = threadIdx.x & 31;
+    if (any && lane < ncta) *cl.map_shared_rank(slot, lane) = stamp;
+    cl.sync();
+    return *slot == stamp;
+}
+
+template <int TY, int TX, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) svf_grid5_cluster_kernel(const SvfBatch bt, const int n, const int R) {
+    using Cfg = Grid5Cfg<TY, TX, MAXT>;
+    constexpr int C = Cfg::C, K = 5, A = 4, STRIDE = Cfg::STRIDE;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int *votes = reinterpret_cast<int *>(smem_raw + 2 * STRIDE);      // [0..1] continue stamps, [2..3] non-finite stamps
+    cgx::cluster_group cl = cgx::this_cluster();
+    const int ncta = (int)cl.num_blocks(), crank = (int)cl.block_rank();
+
+    SvfArgs a = bt.a;
+    offset_svf(a, bt, blockIdx.x / ncta);
+    const int S = a.S, tid = threadIdx.x;
+    const int ntx = n / TX;
+    const bool live = tid < ntx * R;
+    const int tx = live ? tid % ntx : 0, lty = live ? tid / ntx : 0;
+    const int gty = crank * R + lty, nty = n / TY;
+
+    double w[C][5], p0r[C], cur[C];
+    const uint32_t slot = 8u * Cfg::PITCH;
+    const uint32_t own = slot * tid;
+    const uint32_t nb_lf = (live && tx > 0) ? own - slot : own;
+    const uint32_t nb_rt = (live && tx < ntx - 1) ? own + slot : own;
+    const unsigned char *up_p = smem_raw + own, *dn_p = smem_raw + own;
+    if (live && lty > 0) up_p = smem_raw + own - slot * ntx;
+    else if (live && gty > 0) up_p = cl.map_shared_rank(smem_raw, crank - 1) + slot * ((R - 1) * ntx + tx);
+    if (live && lty < R - 1) dn_p = smem_raw + own + slot * ntx;
+    else if (live && gty < nty - 1) dn_p = cl.map_shared_rank(smem_raw, crank + 1) + slot * tx;
+
+#pragma unroll
+    for (int iy = 0; iy < TY; ++iy)
+#pragma unroll
+        for (int ix = 0; ix < TX; ++ix) {
+            const int c = iy * TX + ix;
+            const int s = (gty * TY + iy) * n + tx * TX + ix;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) w[c][k] = 0.0;
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const int pred = a.idx[(size_t)j * S + s];
+                    double acc = 0.0;
+#pragma unroll
+                    for (int aa = 0; aa < A; ++aa)
+                        acc = fma(__ldg(a.p + ((size_t)aa * K + j) * S + s), a.policy[(size_t)pred * A + aa], acc);
+                    if (a.term[pred]) acc = 0.0;
+                    const int off = pred - s;
+                    w[c][0] += (off == -n) ? acc : 0.0;
+                    w[c][1] += (off == -1) ? acc : 0.0;
+                    w[c][2] += (off == 0) ? acc : 0.0;
+                    w[c][3] += (off == 1) ? acc : 0.0;
+                    w[c][4] += (off == n) ? acc : 0.0;
+                }
+            }
+            p0r[c] = live ? a.p0[s] : 0.0;
+            cur[c] = 0.0;
+            *reinterpret_cast<double *>(smem_raw + own + 8 * c) = 0.0;
+            *reinterpret_cast<double *>(smem_raw + own + 8 * c + STRIDE) = 0.0;
+        }
+    if (tid < 4) votes[tid] = 0;
+    cl.sync();
+
+    const double eps = a.eps;
+    const int limit = a.max_sweeps > 0 ? a.max_sweeps : 0x7fffffff;
+    int nsw = 0, status = IRLB200_ST_CONVERGED;
+    for (;;) {
+        double x[C];
+        if (nsw & 1) svf_grid5_cluster_sweep<TY, TX, STRIDE, 0>(smem_raw, own, up_p, dn_p, nb_lf, nb_rt, w, p0r, cur, x);
+        else svf_grid5_cluster_sweep<TY, TX, 0, STRIDE>(smem_raw, own, up_p, dn_p, nb_lf, nb_rt, w, p0r, cur, x);
+        ++nsw;
+        bool stop = false;
+        // sampled vote first (one cell per tile), full test only when it finds nothing -- see svf_grid5_kernel
+        if (!cluster_any(cl, votes, 2 * nsw, !(fabs(x[0] - cur[0]) <= eps), ncta)) {
+            bool go = false;
+#pragma unroll
+            for (int c = 1; c < C; ++c) go |= !(fabs(x[c] - cur[c]) <= eps);
+            stop = !cluster_any(cl, votes, 2 * nsw + 1, go, ncta);
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) cur[c] = x[c];
+        if (stop) break;
+        if ((nsw & 15) == 0) {
+            bool bad = false;
+#pragma unroll
+            for (int c = 0; c < C; ++c) bad |= (cur[c] - cur[c]) != 0.0;
+            if (cluster_any(cl, votes + 2, nsw, bad, ncta)) { status = IRLB200_ST_NONFINITE; break; }
+        }
+        if (nsw >= limit) { status = IRLB200_ST_MAXSWEEPS; break; }
+    }
+
+    if (live) {
+#pragma unroll
+        for (int iy = 0; iy < TY; ++iy)
+#pragma unroll
+            for (int ix = 0; ix < TX; ++ix) {
+                const int c = iy * TX + ix;
+                const int s = (gty * TY + iy) * n + tx * TX + ix;
+                a.svf[s] = cur[c];
+                if (a.grad) a.grad[s] = a.e_features[s] - cur[c];
+            }
+    }
+    if (tid == 0 && crank == 0) {
+        const size_t wb = blockIdx.x / ncta;
+        if (bt.n_iter) bt.n_iter[wb * bt.out_stride] = nsw;
+        if (bt.status) bt.status[wb * bt.out_stride] = status;
+    }
+    cl.sync();      // no CTA may exit while a neighbour can still read its shared memory
+}
+
+// ---------------------------------------------------------------------------
 // Stencil-tiled non-causal backward pass (local_action_probabilities, maxent.py:119-159).
 //
 // All but the last of the n_sweeps partition sweeps only carry zs forward, and
@@ -674,6 +844,45 @@ static int launch_backward_grid5(const SuccBatch &bt, int B, int n, cudaStream_t
     if (int rc = prep_smem(k, sm)) return rc;
     k<<<B, round_up32((n / TX) * (n / TY)), sm, st>>>(bt, n);
     return IRLB200_OK;
+}
+
+// cluster launch of the tiled forward pass: B worlds, `ncta` CTAs each
+static int launch_svf_grid5_cluster(const SvfBatch &bt, int B, int n, int ncta, cudaStream_t st) {
+    using Cfg = Grid5Cfg<2, 4, 256>;
+    auto k = svf_grid5_cluster_kernel<2, 4, 256>;
+    const int ntx = n / 4, nty = n / 2, R = nty / ncta;
+    const size_t sm = 2 * (size_t)Cfg::STRIDE + 32;
+    if (int rc = prep_smem(k, sm)) return rc;
+    if (ncta > 8) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(non-portable cluster)");
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(B * ncta));
+    cfg.blockDim = dim3((unsigned)round_up32(ntx * R));
+    cfg.dynamicSmemBytes = sm;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)ncta;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k, bt, n, R);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaLaunchKernelEx(svf cluster)");
+    return IRLB200_OK;
+}
+
+// pick a cluster size for an n x n world: tile rows must split evenly, <= 256 threads per CTA
+static int cluster_size_for(int n) {
+    if (n % 4 || n % 2) return 0;
+    const int ntx = n / 4, nty = n / 2;
+    for (int c : {2, 4, 8, 16}) {
+        if (nty % c) continue;
+        if (ntx * (nty / c) <= 256) return c;
+    }
+    return 0;
 }
 
 // ---- CTA: successor phases --------------------------------------------------
@@ -937,7 +1146,8 @@ static int max_states_cta_impl() {
 }
 
 extern "C" int irlb200_max_states_cta(void) { return max_states_cta_impl(); }
-extern "C" int irlb200_max_states_cluster(void) { return 0; }   // cluster mode: not built yet
+// cluster mode exists for the forward pass of grid-stencil tables: 16 CTAs x 256 tiles x 8 cells
+extern "C" int irlb200_max_states_cluster(void) { return 16 * 256 * 8; }
 
 static int check_tables(const irlb200_tables *t, bool need_succ, bool need_pred) {
     if (!t) return fail(IRLB200_EINVAL, "tables == NULL");
@@ -1039,7 +1249,15 @@ extern "C" int irlb200_svf(const irlb200_tables *t, int B, const double *p_initi
     if (int rc = check_tables(t, false, true)) return rc;
     if (B <= 0 || !p_initial || !terminal_mask || !policy || !svf) return fail(IRLB200_EINVAL, "svf: bad argument");
     if (grad && !e_features) return fail(IRLB200_EINVAL, "svf: grad requested without e_features");
-    if (int rc = pick_mode(mode, B, t->S, t->A, false, &mode)) return rc;
+    // thread-block-cluster mode: grid-stencil tables whose tile rows split evenly over <= 16 CTAs
+    const int cl_size = (t->stencil_n > 0 && t->stencil_n * t->stencil_n == t->S && t->A == 4 && t->Kp == 5)
+                            ? cluster_size_for(t->stencil_n) : 0;
+    const bool want_cluster = mode == IRLB200_MODE_CLUSTER ||
+                              (mode == IRLB200_MODE_AUTO && cl_size > 0 && t->S > 2048 && B <= 64);
+    if (mode == IRLB200_MODE_CLUSTER && cl_size == 0)
+        return fail(IRLB200_ELIMIT, "cluster mode needs grid-stencil tables with n <= 128, n % 4 == 0");
+    if (!want_cluster)
+        if (int rc = pick_mode(mode, B, t->S, t->A, false, &mode)) return rc;
     SvfBatch bt{};
     fill_svf(bt.a, t);
     bt.a.p0 = p_initial; bt.a.term = terminal_mask; bt.a.policy = policy; bt.a.eps = eps;
@@ -1050,6 +1268,10 @@ extern "C" int irlb200_svf(const irlb200_tables *t, int B, const double *p_initi
     bt.term_stride = mask_shared ? 0 : (size_t)t->S;
     bt.ef_stride = ef_shared ? 0 : (size_t)t->S;
     bt.n_iter = n_iter; bt.status = status; bt.out_stride = 1;
+    if (want_cluster) {
+        if (device_count_impl() <= 0) return fail(IRLB200_ECUDA, "no CUDA device");
+        return launch_svf_grid5_cluster(bt, B, t->stencil_n, cl_size, (cudaStream_t)stream);
+    }
     if (mode == IRLB200_MODE_CTA) return launch_svf_cta(bt, B, (cudaStream_t)stream);
     return launch_svf_grid(bt.a, n_iter, status, (cudaStream_t)stream);
 }

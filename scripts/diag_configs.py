@@ -23,9 +23,9 @@ t = E.gridworld_tables(n, 0.2)
 p0 = np.zeros(Sn); p0[0] = 1.0
 mask, phi = E.terminal_mask([Sn - 1], Sn), E.terminal_phi([Sn - 1], Sn)
 rg = np.full(Sn, -0.1); rg[Sn - 1] = 1.0
-for mode, nm in ((E.MODE_GRID, "grid"),):
+for mode, nm in ((E.MODE_GRID, "grid"), (E.MODE_CLUSTER, "cluster")):
     torch.cuda.synchronize(); t0 = time.time()
-    pol = E.soft_vi(t, phi, rg, 0.9, mode=mode); torch.cuda.synchronize(); t1 = time.time()
+    pol = E.soft_vi(t, phi, rg, 0.9, mode=E.MODE_GRID); torch.cuda.synchronize(); t1 = time.time()
     nl = E.last_info.counts()[0]
     d = E.svf(t, p0, mask, pol[0], 1e-5, max_sweeps=400000, mode=mode); torch.cuda.synchronize(); t2 = time.time()
     ns = E.last_info.counts()[0]

@@ -526,3 +526,33 @@ def test_peer_slab_single_rank():
         assert g.last_n_iter == 25 and g.last_status == E.ST_MAXSWEEPS
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("n", [16, 64, 128])
+def test_cluster_mode_forward_pass(n):
+    """Thread-block-cluster (DSMEM) forward pass == cooperative-grid forward pass, bitwise, same count."""
+    S = n * n
+    t = E.gridworld_tables(n, 0.2)
+    r = np.full(S, -0.1); r[S - 1] = 1.0
+    p0 = np.zeros(S); p0[0] = 1.0
+    mask, phi = E.terminal_mask([S - 1], S), E.terminal_phi([S - 1], S)
+    pol = E.soft_vi(t, phi, r, 0.9)
+    budget = None if n <= 64 else 30000
+    d_c = E.svf(t, p0, mask, pol, 1e-5, max_sweeps=budget, mode=E.MODE_CLUSTER)
+    n_c, st_c = counts()[0], E.last_info.stati()[0]
+    d_g = E.svf(t, p0, mask, pol, 1e-5, max_sweeps=budget, mode=E.MODE_GRID)
+    assert counts()[0] == n_c and E.last_info.stati()[0] == st_c
+    assert (d_c == d_g).all()
+    if n == 16:
+        mdp = SP.icy_gridworld_sparse(n, 0.2)
+        dref, n_ref = SP.expected_svf_from_policy(mdp, p0, [S - 1], pol[0].cpu().numpy())
+        assert n_c == n_ref
+        close(d_c[0], dref)
+    # batch of clusters
+    d_b = E.svf(t, p0, mask, torch_stack2(pol), 1e-5, max_sweeps=budget, mode=E.MODE_CLUSTER)
+    assert (d_b[0] == d_c[0]).all() and (d_b[1] == d_c[0]).all()
+
+
+def torch_stack2(pol):
+    import torch
+    return torch.cat([pol, pol], 0)
