@@ -151,6 +151,19 @@ def cpu_full_body(w, b):
     return dt, n_svf
 
 
+def cpu_sparse_body(w, b):
+    """The same body with the scipy-CSR restatement (oracle/sparse_port.py): NOT the reference's cost
+    profile -- the "fair sparse CPU" line of BASELINE.md section 3, one thread."""
+    from oracle import sparse_port as SP
+    mdp = SP.icy_gridworld_sparse(w["n"], w["p_slip"][b])
+    mdp.transposed()
+    t0 = time.perf_counter()
+    pa = SP.local_action_probabilities(mdp, w["terminal"], w["theta0"][b], rescale=False)
+    d, n_svf = SP.expected_svf_from_policy(mdp, w["p0"], w["terminal"], pa, 1e-5)
+    _ = w["theta0"][b] + 1e-3 * (0.0 - d)
+    return time.perf_counter() - t0, n_svf
+
+
 def cpu_sampled_body(w, b, n_bw=64, n_fw=256):
     """Bounded sample of the same body: the per-call dense slicing / copy of the reference
     (maxent.py:98-102,143) timed in full, n_bw backward and n_fw forward sweeps timed, then
@@ -520,6 +533,10 @@ def run_b200_arm(args):
                                     "sample": "world 0 of the batch, one full gradient-step body with the dense "
                                               "numpy restatement (2S = %d backward + %d forward dense sweeps), "
                                               "%.1f s" % (2 * S, n_svf, t)}
+            ts, _ = cpu_sparse_body(w, 0)
+            line["cpu_baseline"]["sparse_restatement"] = {
+                "value": 1.0 / ts, "unit": UNIT, "cores": 1,
+                "note": "scipy-CSR restatement of the same body (not the reference's dense arithmetic), %.1f s" % ts}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -556,3 +556,78 @@ def test_cluster_mode_forward_pass(n):
 def torch_stack2(pol):
     import torch
     return torch.cat([pol, pol], 0)
+
+
+# ------------------------------------------------------ randomized + edge cases ---
+
+def _random_mdp(rng, S, A, K):
+    P = np.zeros((S, S, A))
+    for s in range(S):
+        for a in range(A):
+            succ = rng.choice(S, size=min(rng.integers(1, K + 1), S), replace=False)
+            w = rng.random(len(succ)) + 0.05
+            P[s, succ, a] = w / w.sum()
+    return P
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_randomized_mdps_against_dense_oracle(seed, variant):
+    """Random shapes (S, A, K), random rewards / start distributions / terminal sets: every kernel
+    against the dense oracle (which is pinned bit-for-bit to the reference)."""
+    rng = np.random.default_rng(1000 + seed)
+    S, A, K = int(rng.integers(2, 70)), int(rng.integers(1, 7)), int(rng.integers(1, 6))
+    P = _random_mdp(rng, S, A, K)
+    term = sorted(set(int(v) for v in rng.choice(S, size=int(rng.integers(1, 3)), replace=False)))
+    r = 0.4 * rng.standard_normal(S) - 0.3
+    p0 = rng.random(S); p0 /= p0.sum()
+    t = E.compress_dense(P)
+    mask, phi = E.terminal_mask(term, S), E.terminal_phi(term, S)
+    ref = D.local_action_probabilities(P, term, r, rescale=True)
+    got = E.backward(t, mask, r, mode=variant)[0].cpu().numpy()
+    ok = np.isfinite(ref)                       # states that cannot reach a terminal are 0/0 in both
+    assert (np.isfinite(got) == ok).all()
+    np.testing.assert_allclose(got[ok], ref[ok], rtol=1e-10)
+    g = 0.5 + 0.45 * rng.random()
+    pc, n_ref = D.local_causal_action_probabilities(P, term, r, g, 1e-6)
+    pol = E.soft_vi(t, phi, r, g, 1e-6, mode=variant)
+    assert counts()[0] == n_ref
+    close(pol[0], pc)
+    damp = 0.9 * pc / np.maximum(pc.sum(axis=1, keepdims=True), 1e-300)
+    dref, n_ref = D.expected_svf_from_policy(P, p0, term, damp, 1e-6)
+    d = E.svf(t, p0, mask, damp, 1e-6, mode=variant)
+    assert counts()[0] == n_ref
+    close(d[0], dref)
+    vref, n_ref = D.value_iteration(P, r, g, 1e-6)
+    v = E.value_iteration(t, r, g, 1e-6, mode=variant)
+    assert counts()[0] == n_ref
+    close(v[0], vref)
+
+
+def test_edge_cases():
+    """One-state world, empty terminal set, zero start mass, huge eps, zero sweeps."""
+    P1 = np.ones((1, 1, 2))
+    t = E.compress_dense(P1)
+    v = E.value_iteration(t, np.array([0.5]), 0.5, 1e-9)
+    vref, n = D.value_iteration(P1, np.array([0.5]), 0.5, 1e-9)
+    assert counts()[0] == n
+    close(v[0], vref)
+    P = D.icy_gridworld_table(4, 0.2)
+    t = E.compress_dense(P)
+    S = 16
+    # zero start mass: the first sweep already changes nothing -> exactly one sweep (SURVEY 9.6)
+    d = E.svf(t, np.zeros(S), E.terminal_mask([15], S), np.full((S, 4), 0.25), 1e-5)
+    assert counts()[0] == 1 and (d == 0).all()
+    # huge eps: one sweep, result = p0
+    p0 = np.zeros(S); p0[3] = 1.0
+    d = E.svf(t, p0, E.terminal_mask([15], S), np.full((S, 4), 0.25), 10.0)
+    dref, n = D.expected_svf_from_policy(P, p0, [15], np.full((S, 4), 0.25), 10.0)
+    assert counts()[0] == n == 1
+    close(d[0], dref)
+    # empty terminal set: causal policy rows all sum to 1, value iteration unaffected
+    pc, n = D.local_causal_action_probabilities(P, [], np.linspace(-1, 0, S), 0.8, 1e-6)
+    pol = E.soft_vi(t, E.terminal_phi([], S), np.linspace(-1, 0, S), 0.8, 1e-6)
+    assert counts()[0] == n
+    close(pol[0], pc)
+    # backward pass with an explicit sweep count (the reference hard-codes 2*S)
+    ref = D.local_action_probabilities(P, [15], np.full(S, -1.0))
+    close(E.backward(t, E.terminal_mask([15], S), np.full(S, -1.0), n_sweeps=2 * S)[0], ref)
