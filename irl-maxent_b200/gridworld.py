@@ -96,6 +96,33 @@ class GridWorld:
     def _transition_prob(self, s_from, s_to, a):
         return self.p_transition[s_from, s_to, a]
 
+    def successors(self, s, a):
+        """Sparse row of the transition model: (states, probabilities) of the non-zero entries of
+        p_transition[s, :, a], states ascending -- without touching the dense table.  The values
+        are formed by the same expressions as the table, so they are bit-identical to it."""
+        n = self.size
+        x, y = s % n, s // n
+        ax, ay = self.actions[a]
+        xb, yb = x in (0, n - 1), y in (0, n - 1)
+        v_int, v_other = self._neighbour_values(a)
+        inside = 0 <= x + ax < n and 0 <= y + ay < n
+        stay = self._self_loop_values_scalar(not inside, xb and yb, xb or yb)
+        out_s, out_p = [], []
+        for t, (dx, dy) in ((s - n, (0, -1)), (s - 1, (-1, 0)), (s, (0, 0)), (s + 1, (1, 0)), (s + n, (0, 1))):
+            if (dx, dy) == (0, 0):
+                p = stay
+            elif not (0 <= x + dx < n and 0 <= y + dy < n):
+                continue
+            else:
+                p = v_int if (dx, dy) == (ax, ay) else v_other
+            if p != 0.0:
+                out_s.append(t)
+                out_p.append(p)
+        return np.array(out_s, dtype=np.int64), np.array(out_p)
+
+    def _self_loop_values_scalar(self, into_wall, corner, edge):
+        return 1.0 if into_wall else 0.0
+
     def tables(self):
         """Device-resident compressed tables, built without the dense detour."""
         if self._tables is None:
@@ -131,12 +158,39 @@ class IcyGridWorld(GridWorld):
         stay[~into_wall & ~corner & edge] = p / nA
         return stay
 
+    def _self_loop_values_scalar(self, into_wall, corner, edge):
+        p, nA = self.p_slip, self.n_actions
+        if into_wall:
+            return 1.0 - p + 2.0 * p / nA if corner else 1.0 - p + p / nA
+        if corner:
+            return 2.0 * p / nA
+        return p / nA if edge else 0.0
+
     def __repr__(self):
         return "IcyGridWorld(size={}, p_slip={})".format(self.size, self.p_slip)
 
 
-def state_features(world):
-    """One indicator feature per state: the S x S identity (reference: gridworld.py:254-268)."""
+class IdentityFeatures:
+    """The S x S identity feature matrix of `state_features` without the S^2 storage (2.1 GB at
+    128 x 128).  `maxent.irl` / `irl_causal` recognise it and skip both feature products
+    (features.dot(theta) == theta, features.T.dot(svf) == svf, bit for bit)."""
+
+    def __init__(self, n_states):
+        self.shape = (n_states, n_states)
+        self.ndim = 2
+
+    def dot(self, theta):
+        return theta
+
+    def __array__(self, dtype=None, copy=None):
+        return np.identity(self.shape[0], dtype=dtype or float)
+
+
+def state_features(world, implicit=None):
+    """One indicator feature per state: the S x S identity (reference: gridworld.py:254-268).
+    For worlds above 4 096 states (or implicit=True) an `IdentityFeatures` stand-in is returned."""
+    if implicit or (implicit is None and world.n_states > 4096):
+        return IdentityFeatures(world.n_states)
     return np.identity(world.n_states)
 
 

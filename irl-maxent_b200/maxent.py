@@ -41,6 +41,8 @@ def _out(t, as_tensor):
 
 
 def _is_identity(features):
+    if type(features).__name__ == "IdentityFeatures":
+        return True
     if E.is_tensor(features):
         return False        # checked on the host only; tensors go through the dense kernels
     f = np.asarray(features)
@@ -53,6 +55,15 @@ def feature_expectation_from_trajectories(features, trajectories):
     """Mean over trajectories of the summed feature rows of every visited state
     (reference: maxent.py:15-39).  Accumulates in visiting order, so the result is
     bit-identical with the reference's running sum.  Host side, once per irl call."""
+    if type(features).__name__ == "IdentityFeatures":
+        # identity rows: the running sum of one-hot rows is a visit count (exact in float64)
+        fe = np.zeros(features.shape[1])
+        n = 0
+        for t in trajectories:
+            for s in t.states():
+                fe[s] += 1.0
+            n += 1
+        return fe / n
     f = features.cpu().numpy() if E.is_tensor(features) else np.asarray(features)
     fe = np.zeros(f.shape[1])
     n = 0

@@ -28,13 +28,30 @@ class Trajectory:
         return "{}".format(self._t)
 
 
+def _choice_sparse(states, probs):
+    """`np.random.choice(range(S), p=row)` for a row given by its non-zero entries (ascending).
+    numpy draws ONE uniform and searches the normalised cumulative sum from the right; zero entries
+    only repeat cdf values, so searching the cdf of the non-zeros picks the same state and leaves
+    the global generator in the same state as the dense call -- seeded runs stay bit-identical."""
+    cdf = np.cumsum(probs)
+    cdf /= cdf[-1]
+    u = np.random.random_sample()
+    return int(states[np.searchsorted(cdf, u, side='right')])
+
+
 def generate_trajectory(world, policy, start, final):
-    """Roll `policy` out from `start` until a state in `final` (reference: trajectory.py:52-87)."""
+    """Roll `policy` out from `start` until a state in `final` (reference: trajectory.py:52-87).
+    Worlds that expose `successors(s, a)` are sampled from their sparse rows in O(1) per step
+    instead of an O(S) dense row (the dense table of a large world does not exist)."""
     state, steps = start, []
+    sparse = hasattr(world, "successors")
     states = range(world.n_states)
     while state not in final:
         action = policy(state)
-        nxt = np.random.choice(states, p=world.p_transition[state, :, action])
+        if sparse:
+            nxt = _choice_sparse(*world.successors(state, action))
+        else:
+            nxt = np.random.choice(states, p=world.p_transition[state, :, action])
         steps.append((state, action, nxt))
         state = nxt
     return Trajectory(steps)

@@ -582,7 +582,8 @@ def test_randomized_mdps_against_dense_oracle(seed, variant):
     p0 = rng.random(S); p0 /= p0.sum()
     t = E.compress_dense(P)
     mask, phi = E.terminal_mask(term, S), E.terminal_phi(term, S)
-    ref = D.local_action_probabilities(P, term, r, rescale=True)
+    with np.errstate(invalid="ignore"):         # unreachable states are 0/0 in the reference too
+        ref = D.local_action_probabilities(P, term, r, rescale=True)
     got = E.backward(t, mask, r, mode=variant)[0].cpu().numpy()
     ok = np.isfinite(ref)                       # states that cannot reach a terminal are 0/0 in both
     assert (np.isfinite(got) == ok).all()
@@ -631,3 +632,30 @@ def test_edge_cases():
     # backward pass with an explicit sweep count (the reference hard-codes 2*S)
     ref = D.local_action_probabilities(P, [15], np.full(S, -1.0))
     close(E.backward(t, E.terminal_mask([15], S), np.full(S, -1.0), n_sweeps=2 * S)[0], ref)
+
+
+def test_irl_on_a_large_lazy_world_with_implicit_features():
+    """End-to-end irl / irl_causal on a world handle (no dense table, no dense features): trajectories
+    from the sparse sampler, tables built on the device, identity features implicit.  Checked
+    against the dense oracle at 12x12 with the same trajectories."""
+    n = 12
+    Sn = n * n
+    world = W.IcyGridWorld(n, 0.2, dense=False)
+    np.random.seed(3)
+    r_true = np.full(Sn, -0.1); r_true[Sn - 1] = 1.0
+    value = S.value_iteration(world.tables(), r_true, 0.9)
+    policy = S.stochastic_policy_from_value(world, value, w=lambda x: np.exp(4 * x))
+    initial = np.zeros(Sn); initial[0] = 1.0
+    tjs = list(T.generate_trajectories(40, world, T.stochastic_policy_adapter(policy), initial, [Sn - 1]))
+    assert world._dense is None, "the sampler must not build the dense table"
+    F = W.state_features(world, implicit=True)
+    opt = O.ExpSga(lr=O.linear_decay(lr0=0.2))
+    r = M.irl_causal(world.tables(), F, [Sn - 1], tjs, opt, O.Constant(1.0), 0.9, eps=1e-3)
+    # oracle on the dense table with the same statistics
+    P = D.icy_gridworld_table(n, 0.2)
+    ef = D.feature_expectation_from_trajectories(np.identity(Sn), tjs)
+    p0 = D.initial_probabilities_from_trajectories(Sn, tjs)
+    ref, n_ref, _ = D.irl_causal(P, np.identity(Sn), [Sn - 1], ef, p0, D.ExpSgaPort(D.linear_decay(0.2)), np.ones(Sn),
+                                 0.9, eps=1e-3)
+    assert opt.k == n_ref
+    close(r, ref)

@@ -186,3 +186,42 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.lower(), \
                     "%s mentions the oracle" % os.path.join(dirpath, f)
+
+
+# ------------------------------------------ sparse sampler / implicit features ---
+
+def test_sparse_rows_equal_dense_rows():
+    for world in (W.IcyGridWorld(5, 0.2), W.IcyGridWorld(2, 0.35), W.GridWorld(4), W.IcyGridWorld(1, 0.2)):
+        P = world.p_transition
+        for s in range(world.n_states):
+            for a in range(world.n_actions):
+                idx, p = world.successors(s, a)
+                nz = np.nonzero(P[s, :, a])[0]
+                assert np.array_equal(idx, nz) and np.array_equal(p, P[s, nz, a])
+
+
+def test_sparse_sampler_consumes_rng_like_dense_choice(golden):
+    """The O(1) sampler reproduces the reference's seeded trajectories bit for bit."""
+    g = golden("e2e_5x5")
+    world = W.IcyGridWorld(5, 0.2)
+    np.random.seed(0)
+    initial = np.zeros(25); initial[0] = 1.0
+    tjs = list(T.generate_trajectories(200, world, T.stochastic_policy_adapter(g["expert_policy"]), initial, [24]))
+    assert [t.transitions() for t in tjs] == [t.transitions() for t in load_trajectories(g)]
+    # and against numpy's own dense draw, state by state
+    rng_state = np.random.get_state()
+    a = T._choice_sparse(*world.successors(7, 2))
+    np.random.set_state(rng_state)
+    b = np.random.choice(range(25), p=world.p_transition[7, :, 2])
+    assert a == b
+
+
+def test_implicit_identity_features(golden):
+    import maxent as M
+    g = golden("e2e_5x5")
+    tjs = load_trajectories(g)
+    F = W.state_features(W.IcyGridWorld(5), implicit=True)
+    assert F.shape == (25, 25) and M._is_identity(F)
+    assert np.array_equal(M.feature_expectation_from_trajectories(F, tjs), g["e_features"])
+    big = W.IcyGridWorld(128)
+    assert isinstance(W.state_features(big), W.IdentityFeatures) and big._dense is None
