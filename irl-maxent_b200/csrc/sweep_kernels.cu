@@ -1252,8 +1252,11 @@ extern "C" int irlb200_svf(const irlb200_tables *t, int B, const double *p_initi
     // thread-block-cluster mode: grid-stencil tables whose tile rows split evenly over <= 16 CTAs
     const int cl_size = (t->stencil_n > 0 && t->stencil_n * t->stencil_n == t->S && t->A == 4 && t->Kp == 5)
                             ? cluster_size_for(t->stencil_n) : 0;
+    // AUTO: small batches of mid-size worlds (one world cannot fill an SM's latency budget), and every
+    // world that does not fit one CTA's shared memory
     const bool want_cluster = mode == IRLB200_MODE_CLUSTER ||
-                              (mode == IRLB200_MODE_AUTO && cl_size > 0 && t->S > 2048 && B <= 64);
+                              (mode == IRLB200_MODE_AUTO && cl_size > 0 &&
+                               ((t->S > 2048 && B <= 64) || t->S > 8192));
     if (mode == IRLB200_MODE_CLUSTER && cl_size == 0)
         return fail(IRLB200_ELIMIT, "cluster mode needs grid-stencil tables with n <= 128, n % 4 == 0");
     if (!want_cluster)
@@ -1270,7 +1273,11 @@ extern "C" int irlb200_svf(const irlb200_tables *t, int B, const double *p_initi
     bt.n_iter = n_iter; bt.status = status; bt.out_stride = 1;
     if (want_cluster) {
         if (device_count_impl() <= 0) return fail(IRLB200_ECUDA, "no CUDA device");
-        return launch_svf_grid5_cluster(bt, B, t->stencil_n, cl_size, (cudaStream_t)stream);
+        const int rc = launch_svf_grid5_cluster(bt, B, t->stencil_n, cl_size, (cudaStream_t)stream);
+        if (rc == IRLB200_OK || mode == IRLB200_MODE_CLUSTER) return rc;
+        // AUTO only: this device cannot schedule the cluster shape -> cooperative grid (same results)
+        cudaGetLastError();
+        if (int rc2 = pick_mode(IRLB200_MODE_AUTO, B, t->S, t->A, false, &mode)) return rc2;
     }
     if (mode == IRLB200_MODE_CTA) return launch_svf_cta(bt, B, (cudaStream_t)stream);
     return launch_svf_grid(bt.a, n_iter, status, (cudaStream_t)stream);

@@ -659,3 +659,27 @@ def test_irl_on_a_large_lazy_world_with_implicit_features():
                                  0.9, eps=1e-3)
     assert opt.k == n_ref
     close(r, ref)
+
+
+def test_irl_batch_equals_individual_runs(golden):
+    """Hyper-parameter sweep in lockstep == the same candidates run one by one (same kernels):
+    identical outer step counts, rewards equal to rounding; candidate 0 is main.py's setting and
+    reproduces the reference's 375 steps."""
+    g = golden("e2e_5x5")
+    tabs = E.gridworld_tables(5, 0.2)
+    ef, p0 = g["e_features"], g["p_initial"]
+    make = [lambda: O.ExpSga(lr=O.linear_decay(lr0=0.2)), lambda: O.ExpSga(lr=O.linear_decay(lr0=0.1)),
+            lambda: O.ExpSga(lr=O.power_decay(lr0=0.3)), lambda: O.ExpSga(lr=0.05),
+            lambda: O.ExpSga(lr=O.exponential_decay(lr0=0.2, decay_rate=0.01))]
+    rewards, steps = M.irl_batch(tabs, [24], ef, p0, [m() for m in make], O.Constant(1.0))
+    assert steps[0] == int(g["irl_steps"]) == 375
+    close(rewards[0], g["irl_reward"])
+    for b, m in enumerate(make):
+        r1, s1 = M.irl_batch(tabs, [24], ef, p0, [m()], O.Constant(1.0))
+        assert s1[0] == steps[b]
+        close(rewards[b], r1[0].cpu().numpy(), rtol=1e-12)
+    # causal variant with per-candidate worlds
+    tabs2 = E.gridworld_tables(5, [0.2, 0.3])
+    rc, sc = M.irl_batch(tabs2, [24], ef, p0, [make[0](), make[0]()], O.Constant(1.0), causal=True, discount=0.9)
+    assert sc[0] == int(g["irl_causal_0.9_steps"])
+    close(rc[0], g["irl_causal_0.9_reward"])
