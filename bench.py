@@ -311,6 +311,22 @@ def other_configs():
         "algorithmic_GBps": (n_lap * BWD_BYTES_PER_STATE_SWEEP + n_svf * SVF_BYTES_PER_STATE_SWEEP) * S / best / 1e9,
         "note": "sync-latency bound: 3.5 MB of tables are register resident; soft-VI in cooperative-grid mode (one "
                 "grid barrier per sweep), forward pass in thread-block-cluster mode (DSMEM halos, barrier.cluster)"}
+    # C2 as a batch: 1024 independent copies of the 5x5 causal IRL problem in lockstep (irl_batch)
+    try:
+        Bc = 1024
+        best = None
+        for _ in range(2):
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            _, st = M.irl_batch(E.gridworld_tables(5, 0.2), [24], np.tile(g["e_features"], (Bc, 1)), g["p_initial"],
+                                O.ExpSga(lr=O.linear_decay(lr0=0.2)), O.Constant(1.0), causal=True, discount=0.9)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t
+            best = dt if best is None else min(best, dt)
+        out["C2_batched_x1024"] = {"candidates": Bc, "outer_steps_each": int(st[0]), "seconds": best,
+                                   "grad_steps_per_s": float(st.sum()) / best}
+    except Exception as e:
+        out["C2_batched_x1024"] = {"error": repr(e)}
     out["C4_causal_batch"] = causal_batch()
     out["roofline_stream"] = stream_roofline()
     return out

@@ -238,45 +238,65 @@ def irl_batch(tables, terminal, e_features, p_initial, optims, init, eps=1e-4, e
     """B independent IRL problems with identity features, run in lockstep on one GPU
     (hyper-parameter sweeps over optimizers / schedules / statistics).
 
-    Candidate b has its own optimizer `optims[b]` (anything with reset / step, e.g. `ExpSga` with a
-    different schedule), its own statistics `e_features[b]`, `p_initial[b]` ([B,S], or [S] shared) and
-    the tables `tables` (one shared world, or B worlds).  Every candidate follows exactly the loop of
-    `irl` / `irl_causal` (maxent.py:240-252 / :436-450): its optimizer steps ITS row of the
-    device-resident omega in place, and it leaves the batch once max|omega_old - omega| <= eps.
-    With a shared world the still-active candidates are compacted before every launch.
+    Candidate b has its own statistics `e_features[b]`, `p_initial[b]` ([B,S], or [S] shared) and the
+    tables `tables` (one shared world, or B worlds).  `optims` is either
+      * a list of B optimizers (anything with reset / step, e.g. `ExpSga` with different schedules):
+        each steps ITS row of the device-resident omega in place, or
+      * ONE optimizer whose step is elementwise (`Sga`, `ExpSga` without `normalize`, no
+        `NormalizeGrad`): it steps the whole [B,S] omega at once; converged rows receive a zero
+        gradient, which leaves them unchanged under both update rules.
+    Every candidate follows exactly the loop of `irl` / `irl_causal` (maxent.py:240-252 / :436-450) and
+    leaves the batch once max|omega_old - omega| <= eps.  With a shared world the still-active
+    candidates are compacted before every launch.
 
     Returns (reward [B,S] device tensor, outer step counts [B] numpy).
     """
     torch = E.require_cuda()
     S = tables.S
-    B = len(optims)
     mask = E.terminal_mask(terminal, S)
     phi = E.terminal_phi(terminal, S) if causal else None
     ef = E.to_device(e_features)
+    per_row = isinstance(optims, (list, tuple))
+    B = len(optims) if per_row else (int(ef.shape[0]) if ef.dim() == 2 else tables.n_tables)
     ef = ef.expand(B, S).contiguous() if ef.dim() == 1 else ef
     p0 = E.to_device(p_initial)
     p0_shared = p0.dim() == 1
     shared_world = tables.n_tables == 1
     theta = torch.stack([E.to_device(init(S)) for _ in range(B)])          # [B, S], omega of every candidate
-    for b, o in enumerate(optims):
-        o.reset(theta[b])                                                   # row views alias theta
+    if per_row:
+        for b, o in enumerate(optims):
+            o.reset(theta[b])                                               # row views alias theta
+    else:
+        optims.reset(theta)
     steps = np.zeros(B, dtype=np.int64)
-    active = list(range(B))
-    while active:
+    active = np.arange(B)
+    while active.size:
         old = theta.clone()
-        if shared_world:
+        compact = shared_world and active.size < B
+        if compact:
             idx = torch.as_tensor(active, device=theta.device)
-            reward = theta.index_select(0, idx)                             # compacted batch
+            reward = theta.index_select(0, idx)
             p0_a = p0 if p0_shared else p0.index_select(0, idx)
             ef_a = ef.index_select(0, idx)
         else:
-            reward, p0_a, ef_a = theta, p0, ef                              # per-world tables: no compaction
+            reward, p0_a, ef_a = theta, p0, ef
         _, grad, _ = E.expected_svf(tables, p0_a, mask, reward, causal=causal, phi=phi,
                                     discount=discount if causal else 0.0, eps_lap=eps_lap, eps_svf=eps_esvf,
                                     e_features=ef_a, fused=False)
-        for j, b in enumerate(active):
-            optims[b].step(grad[j] if shared_world else grad[b])
-            steps[b] += 1
+        if per_row:
+            for j, b in enumerate(active):
+                optims[b].step(grad[j] if compact else grad[b])
+        else:
+            full = torch.zeros_like(theta)
+            if compact:
+                full.index_copy_(0, idx, grad)
+            else:
+                full[torch.as_tensor(active, device=theta.device)] = grad[torch.as_tensor(active, device=theta.device)]
+            optims.step(full)
+        steps[active] += 1
         delta = torch.max(torch.abs(old - theta), dim=1).values.cpu().numpy()   # one host sync per step
-        active = [b for b in active if delta[b] > eps and (max_steps is None or steps[b] < max_steps)]
+        keep = delta[active] > eps
+        if max_steps is not None:
+            keep &= steps[active] < max_steps
+        active = active[keep]
     return theta.clone(), steps

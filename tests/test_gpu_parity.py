@@ -678,6 +678,11 @@ def test_irl_batch_equals_individual_runs(golden):
         r1, s1 = M.irl_batch(tabs, [24], ef, p0, [m()], O.Constant(1.0))
         assert s1[0] == steps[b]
         close(rewards[b], r1[0].cpu().numpy(), rtol=1e-12)
+    # one elementwise optimizer stepping the whole batch at once
+    efb = np.stack([ef, ef, ef])
+    rv, sv = M.irl_batch(tabs, [24], efb, p0, O.ExpSga(lr=O.linear_decay(lr0=0.2)), O.Constant(1.0))
+    assert list(sv) == [375, 375, 375]
+    close(rv[2], g["irl_reward"])
     # causal variant with per-candidate worlds
     tabs2 = E.gridworld_tables(5, [0.2, 0.3])
     rc, sc = M.irl_batch(tabs2, [24], ef, p0, [make[0](), make[0]()], O.Constant(1.0), causal=True, discount=0.9)
