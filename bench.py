@@ -500,6 +500,20 @@ def run_b200_arm(args):
                 "backward": {"launch_ms": bwd_ms, "algorithmic_bytes_per_launch": bwd_bytes,
                              "achieved": bwd_bytes / (bwd_ms / 1e3) / 1e9 if bwd_ms == bwd_ms else None}}
 
+    # the physical roofline of this kernel is on chip: 160 shared-memory wavefronts per 1024-state
+    # world-sweep (2x4 tiles: 12 halo loads + 8 stores of 8 B per thread, 128 B per wavefront, one
+    # wavefront per clock per SM -- scripts/ubench.cu, scripts/ubench_shfl.cu), measured live here
+    try:
+        props = torch.cuda.get_device_properties(local)
+        sm_clock_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
+        cyc = (svf_ms / 1e3) * sm_clock_hz * props.multi_processor_count / float(n_fw.mean())
+        roofline["onchip"] = {"resource": "shared-memory datapath (1 wavefront of 128 B per clock per SM)",
+                              "wavefronts_per_world_sweep": 160.0 * S / 1024.0,
+                              "sm_cycles_per_world_sweep": cyc, "frac": 160.0 * S / 1024.0 / cyc,
+                              "fp64_pipe_cycles_per_world_sweep": 110.0 * S / 1024.0}
+    except Exception:
+        pass
+
     # ---- end to end through the public API with host buffers --------------------
     theta_h = torch.empty((B, S), dtype=torch.float64).pin_memory()
     theta_h.copy_(torch.as_tensor(w["theta0"]))
