@@ -119,8 +119,9 @@ def local_action_probabilities(mdp, terminal, reward, rescale=True):
     return za / zs[:, None]
 
 
-def local_causal_action_probabilities(mdp, terminal, reward, discount, eps=1e-5, max_sweeps=None):
-    """maxent.py:279-341 over CSR.  Returns (policy, n_sweeps)."""
+def local_causal_action_probabilities(mdp, terminal, reward, discount, eps=1e-5, max_sweeps=None,
+                                      return_value=False):
+    """maxent.py:279-341 over CSR.  Returns (policy, n_sweeps) [, v with return_value]."""
     S, A = mdp.n_states, mdp.n_actions
     phi = terminal_reward(terminal, S)
     v = _NEG_HUGE * np.ones(S)
@@ -137,6 +138,8 @@ def local_causal_action_probabilities(mdp, terminal, reward, discount, eps=1e-5,
             n += 1
             if max_sweeps is not None and n >= max_sweeps:
                 break
+        if return_value:
+            return np.exp(q - v[:, None]), n, v
         return np.exp(q - v[:, None]), n
 
 

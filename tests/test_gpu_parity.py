@@ -688,3 +688,111 @@ def test_irl_batch_equals_individual_runs(golden):
     rc, sc = M.irl_batch(tabs2, [24], ef, p0, [make[0](), make[0]()], O.Constant(1.0), causal=True, discount=0.9)
     assert sc[0] == int(g["irl_causal_0.9_steps"])
     close(rc[0], g["irl_causal_0.9_reward"])
+
+
+def test_error_paths_fail_loudly():
+    """Bad requests raise EngineError with the library's message instead of computing something else."""
+    t = E.gridworld_tables(6, [0.2, 0.3])
+    S = 36
+    mask, phi = E.terminal_mask([S - 1], S), E.terminal_phi([S - 1], S)
+    r = np.zeros((2, S))
+    with pytest.raises(E.EngineError, match="one problem per call"):
+        E.soft_vi(t, phi, r, 0.9, mode=E.MODE_GRID)                     # grid mode takes a single problem
+    with pytest.raises(E.EngineError, match="cluster mode"):
+        P = golden_random_P()
+        E.svf(E.compress_dense(P), np.full(7, 1 / 7), E.terminal_mask([6], 7), np.full((7, 3), 0.3),
+              mode=E.MODE_CLUSTER)                                      # no grid stencil -> no cluster kernel
+    with pytest.raises(E.EngineError, match="batch"):
+        E.backward(t, mask, np.zeros((3, S)))                           # 3 problems, 2 tables
+    with pytest.raises(E.EngineError, match="trailing dimension"):
+        E.backward(t, mask, np.zeros((2, S + 1)))
+    with pytest.raises(E.EngineError, match="policy must have shape"):
+        E.svf(t, np.zeros(S), mask, np.zeros((2, S, 3)))
+    with pytest.raises(E.EngineError, match="p_transition must have shape"):
+        E.compress_dense(np.zeros((4, 5, 2)))
+    big_a = np.zeros((3, 3, 17)); big_a[:, 0, :] = 1.0
+    with pytest.raises(E.EngineError, match="run-time A > 16"):
+        E.value_iteration(E.compress_dense(big_a), np.zeros(3), 0.5)
+
+
+def golden_random_P():
+    P = np.zeros((7, 7, 3))
+    for s in range(7):
+        for a in range(3):
+            P[s, (s + a + 1) % 7, a] = 0.6
+            P[s, 6, a] += 0.4
+    return P
+
+
+# ------------------------------------------------------- full BASELINE sizes ---
+
+def test_c3_full_size_counts_and_fixed_point():
+    """C3, 128x128 (16 384 states), goal-directed reward, gamma = 0.9, eps 1e-5: the sweep counts the
+    survey measured with the reference-validated restatement (1 208 soft-VI sweeps,
+    243 869 forward sweeps), and the converged vector satisfies the reference's own update to eps."""
+    n = 128
+    Sn = n * n
+    t = W.IcyGridWorld(n, 0.2).tables()
+    r = np.full(Sn, -0.1); r[Sn - 1] = 1.0
+    p0 = np.zeros(Sn); p0[0] = 1.0
+    mask, phi = E.terminal_mask([Sn - 1], Sn), E.terminal_phi([Sn - 1], Sn)
+    pol = E.soft_vi(t, phi, r, 0.9, 1e-5)
+    assert counts()[0] == 1208
+    rows = pol[0].sum(dim=1).cpu().numpy()
+    np.testing.assert_allclose(np.delete(rows, Sn - 1), 1.0, rtol=1e-9)
+    d = E.svf(t, p0, mask, pol, 1e-5)                      # AUTO -> thread-block-cluster kernel
+    assert counts()[0] == 243869 and E.last_info.stati()[0] == E.ST_CONVERGED
+    mdp = SP.icy_gridworld_sparse(n, 0.2)
+    keep = np.ones(Sn); keep[Sn - 1] = 0.0
+    dn, pn = d[0].cpu().numpy(), pol[0].cpu().numpy()
+    nxt = p0 + sum(mdp.transposed()[a].dot(keep * pn[:, a] * dn) for a in range(4))
+    assert np.max(np.abs(nxt - dn)) <= 1e-5
+    # d[terminal] is the probability mass absorbed so far (SURVEY 9.5); the reference's loose stop rule
+    # (delta <= 1e-5) ends the loop with part of the mass still under way at this size
+    assert 0.5 < dn[Sn - 1] <= 1.0
+
+
+def test_c4_sampled_worlds_of_the_full_batch():
+    """C4: the 4096-world batch of bench.py; three sampled worlds against the sparse oracle
+    (values 1e-10, forward sweep counts exact)."""
+    B, n = 4096, 32
+    Sn = n * n
+    ps = 0.1 + 0.2 * np.arange(B) / 4096.0
+    tabs = E.gridworld_tables(n, ps)
+    theta = -np.log(4.0) + 0.01 * np.random.default_rng(1000).standard_normal((B, Sn))
+    p0 = np.zeros(Sn); p0[0] = 1.0
+    d, _ = M.compute_expected_svf_batch(tabs, p0, [Sn - 1], theta, fused=False, max_sweeps=2000000)
+    nb = E.last_info.counts()
+    assert (E.last_info.stati()[:, 1] == E.ST_CONVERGED).all()
+    for b in (0, 1777, 4095):
+        mdp = SP.icy_gridworld_sparse(n, ps[b])
+        pa = SP.local_action_probabilities(mdp, [Sn - 1], theta[b])
+        dref, n_ref = SP.expected_svf_from_policy(mdp, p0, [Sn - 1], pa, 1e-5)
+        assert nb[b, 1] == n_ref
+        close(d[b], dref)
+
+
+def test_c5_full_size_sweeps_against_sparse_oracle():
+    """C5, 2048x2048 (4.2 M states) on one GPU in streamed cooperative-grid mode: 40 sweeps of soft-VI
+    and of the forward pass against the sparse oracle at full size (1e-10), plus mass bounds."""
+    n = 2048
+    Sn = n * n
+    t = E.gridworld_tables(n, 0.2)
+    rng = np.random.default_rng(5)
+    r = -0.1 + 0.05 * rng.standard_normal(Sn); r[Sn - 1] = 1.0
+    p0 = np.zeros(Sn); p0[0] = 0.5; p0[Sn // 2 + n // 2] = 0.5
+    mask, phi = E.terminal_mask([Sn - 1], Sn), E.terminal_phi([Sn - 1], Sn)
+    mdp = SP.icy_gridworld_sparse(n, 0.2)
+    k = 40
+    pol, val = E.soft_vi(t, phi, r, 0.9, max_sweeps=k, mode=E.MODE_GRID, want_value=True)
+    assert counts()[0] == k and E.last_info.stati()[0] == E.ST_MAXSWEEPS
+    _, _, vref = SP.local_causal_action_probabilities(mdp, [Sn - 1], r, 0.9, max_sweeps=k, return_value=True)
+    # after 40 sweeps most values still carry -1e200 * 0.9^40, so exp(q - v) of a truncated run is not
+    # a meaningful policy (in the reference neither): compare the iterate itself, relatively
+    close(val[0], vref)
+    uniform = np.full((Sn, 4), 0.25)
+    d = E.svf(t, p0, mask, uniform, 1e-5, max_sweeps=k, mode=E.MODE_GRID)
+    dref, _ = SP.expected_svf_from_policy(mdp, p0, [Sn - 1], uniform, 1e-5, max_sweeps=k)
+    close(d[0], dref)
+    dn = d[0].cpu().numpy()
+    assert dn.min() >= 0.0 and dn.sum() <= k + 1e-9 and abs(dn.sum() - k) < 1e-6     # nothing absorbed yet
