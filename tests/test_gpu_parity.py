@@ -796,3 +796,34 @@ def test_c5_full_size_sweeps_against_sparse_oracle():
     close(d[0], dref)
     dn = d[0].cpu().numpy()
     assert dn.min() >= 0.0 and dn.sum() <= k + 1e-9 and abs(dn.sum() - k) < 1e-6     # nothing absorbed yet
+
+
+@pytest.mark.parametrize("n,k", [(8, 7), (8, 16), (12, 33), (32, 1)])
+def test_tiled_kernels_respect_the_sweep_guard(n, k):
+    """Stencil-tiled forward kernel stopped by the guard: exactly k sweeps, iterate == the oracle's
+    k-sweep iterate; the merged-weight backward pass with an explicit sweep count == the oracle's."""
+    Sn = n * n
+    t = E.gridworld_tables(n, 0.25)
+    assert t.stencil_n == n
+    mdp = SP.icy_gridworld_sparse(n, 0.25)
+    p0 = np.zeros(Sn); p0[0] = 0.7; p0[Sn // 2] = 0.3
+    pol = np.random.default_rng(n).dirichlet(np.ones(4), size=Sn)
+    mask = E.terminal_mask([Sn - 1], Sn)
+    d = E.svf(t, p0, mask, pol, 1e-9, max_sweeps=k)
+    assert counts()[0] == k and E.last_info.stati()[0] == E.ST_MAXSWEEPS
+    dref, _ = SP.expected_svf_from_policy(mdp, p0, [Sn - 1], pol, 1e-9, max_sweeps=k)
+    close(d[0], dref)
+    # backward: k sweeps instead of 2S (dense oracle with the same count)
+    P = D.icy_gridworld_table(n, 0.25)
+    r = -1.2 + 0.1 * np.random.default_rng(k).standard_normal(Sn)
+    er = np.exp(r)
+    zs = np.zeros(Sn); zs[Sn - 1] = 1.0
+    for _ in range(k):
+        za = np.array([er * P[:, :, a].dot(zs) for a in range(4)]).T
+        zs = za.sum(axis=1)
+    with np.errstate(invalid="ignore"):
+        ref = za / zs[:, None]
+    got = E.backward(t, mask, r, n_sweeps=k)[0].cpu().numpy()
+    ok = np.isfinite(ref)
+    assert (np.isfinite(got) == ok).all()
+    np.testing.assert_allclose(got[ok], ref[ok], rtol=1e-10)
