@@ -491,7 +491,9 @@ def expected_svf(tables, p_initial, terminal_mask_t, reward, causal=False, phi=N
     r, B = _batch2d(reward, S)
     if fused is None:
         fused = B < 64
-    if fused and (2 + A) * S + 34 > _lib.irlb200_max_states_cta() * 6 + 34:
+    # the fused kernel keeps two iterate buffers and the policy ((2 + A) * S + 34 doubles) in one CTA's
+    # shared memory; irlb200_max_states_cta() quotes that limit for A = 4
+    if fused and (2 + A) * S > 6 * _lib.irlb200_max_states_cta():
         fused = False
     mask, mshared = _maybe_shared(terminal_mask_t, S, B, torch.uint8)
     if not fused:
