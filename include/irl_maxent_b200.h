@@ -35,6 +35,7 @@
 #ifndef IRL_MAXENT_B200_H
 #define IRL_MAXENT_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus

@@ -93,10 +93,10 @@ struct SlabTopo {
     // Two-level barrier.  Memory ordering: every CTA fences at GPU scope before its arrival
     // (cumulative over the CTA's stores, local and peer, via the preceding bar.sync); the last
     // arriver observes all arrivals, issues ONE system-scope fence, then publishes its flag to the
-    // peers with relaxed system-scope stores (release pattern), polls the peers' flags with relaxed
-    // system-scope loads and issues ONE more system fence (acquire pattern) before releasing the
-    // local CTAs at GPU scope.  System-scope operations are slow (~us), so there are exactly two
-    // fences on the critical path and none at all with a single rank.
+    // peers with relaxed system-scope stores (release pattern) and polls the peers' flags with
+    // acquire loads at system scope -- a second full fence would also wait for the acknowledgements of
+    // the flag stores it has just sent over NVLink -- before releasing the local CTAs at GPU scope.
+    // System-scope fences are slow (~1.5 us): one on the critical path, none with a single rank.
     __device__ __forceinline__ unsigned barrier(unsigned long long inc) {
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -117,9 +117,9 @@ struct SlabTopo {
                     bool aborted = false;
                     for (int r = 0; r < G && !aborted; ++r) {
                         if (r == me) continue;
-                        const volatile unsigned long long *f = &sh->flags[par][r];
+                        const unsigned long long *f = &sh->flags[par][r];
                         for (unsigned spins = 0;; ++spins) {
-                            const unsigned long long v = *f;
+                            const unsigned long long v = ld_acquire_sys(f);     // acquire: no full fence needed after
                             if ((v >> 8) == want) { all |= v & 0xFFull; break; }
                             if ((v >> 8) == (~0ull >> 8)) { aborted = true; break; }        // a peer aborted
                             if ((spins & 1023u) == 1023u && (long long)(globaltimer_ns() - t0) > pe->timeout_ns) {
@@ -133,7 +133,6 @@ struct SlabTopo {
                         for (int r = 0; r < G; ++r)
                             if (r != me) *(volatile unsigned long long *)&pe->shared[r]->flags[par][me] = ~0ull;
                     }
-                    __threadfence_system();
                 }
                 sh->slot[(seq + 2u) & 3u] = 0ull;
                 st_release_gpu(&sh->release[s4], (want << 8) | (all & 0xFFull));

@@ -150,6 +150,19 @@ def test_header_and_binding_agree():
     assert set(_declared_symbols()) == set(E.SIGNATURES)
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (and as C++) on its own."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text('#include "irl_maxent_b200.h"\nint main(void) { irlb200_tables t; (void)t; return irlb200_version() > 0 ? 0 : 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)])
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)])
+
+
 def test_library_loads_and_exports_every_symbol():
     """dlopen only -- no compute call (there is no GPU in the CPU test tier)."""
     if not os.path.exists(E.LIB_PATH):
