@@ -238,3 +238,42 @@ def test_implicit_identity_features(golden):
     assert np.array_equal(M.feature_expectation_from_trajectories(F, tjs), g["e_features"])
     big = W.IcyGridWorld(128)
     assert isinstance(W.state_features(big), W.IdentityFeatures) and big._dense is None
+
+
+def test_public_signatures_match_the_reference():
+    """Drop-in contract: names, argument order, keyword names and defaults of
+    the reference's public functions (note `eps_esvf` in irl vs `eps_svf` in irl_causal)."""
+    import inspect
+    import maxent as M
+    import solver as S
+    expected = {
+        (M, "irl"): "(p_transition, features, terminal, trajectories, optim, init, eps=0.0001, eps_esvf=1e-05)",
+        (M, "irl_causal"): "(p_transition, features, terminal, trajectories, optim, init, discount, eps=0.0001, "
+                           "eps_svf=1e-05, eps_lap=1e-05)",
+        (M, "compute_expected_svf"): "(p_transition, p_initial, terminal, reward, eps=1e-05)",
+        (M, "compute_expected_causal_svf"): "(p_transition, p_initial, terminal, reward, discount, eps_lap=1e-05, "
+                                            "eps_svf=1e-05)",
+        (M, "local_action_probabilities"): "(p_transition, terminal, reward)",
+        (M, "local_causal_action_probabilities"): "(p_transition, terminal, reward, discount, eps=1e-05)",
+        (M, "expected_svf_from_policy"): "(p_transition, p_initial, terminal, p_action, eps=1e-05)",
+        (M, "softmax"): "(x1, x2)",
+        (M, "feature_expectation_from_trajectories"): "(features, trajectories)",
+        (M, "initial_probabilities_from_trajectories"): "(n_states, trajectories)",
+        (S, "value_iteration"): "(p, reward, discount, eps=0.001)",
+        (S, "stochastic_value_iteration"): "(p, reward, discount, eps=0.001)",
+        (S, "optimal_policy_from_value"): "(world, value)",
+        (S, "optimal_policy"): "(world, reward, discount, eps=0.001)",
+        (T, "generate_trajectory"): "(world, policy, start, final)",
+        (T, "generate_trajectories"): "(n, world, policy, start, final)",
+        (O, "linear_decay"): "(lr0=0.2, decay_rate=1.0, decay_steps=1)",
+        (O, "power_decay"): "(lr0=0.2, decay_rate=1.0, decay_steps=1, power=2)",
+        (O, "exponential_decay"): "(lr0=0.2, decay_rate=0.5, decay_steps=1)",
+    }
+    for (mod, name), sig in expected.items():
+        assert str(inspect.signature(getattr(mod, name))) == sig, name
+    assert str(inspect.signature(S.stochastic_policy_from_value)).startswith("(world, value, w=")
+    assert str(inspect.signature(O.ExpSga.__init__)) == "(self, lr, normalize=False)"
+    assert str(inspect.signature(O.Sga.__init__)) == "(self, lr)"
+    assert str(inspect.signature(O.Uniform.__init__)) == "(self, low=0.0, high=1.0)"
+    assert str(inspect.signature(O.Constant.__init__)) == "(self, value=1.0)"
+    assert str(inspect.signature(W.IcyGridWorld.__init__)).startswith("(self, size, p_slip=0.2")
