@@ -225,6 +225,9 @@ int irlb200_slab_weights(int cnt, int A, int K, const int32_t *pred_idx, const d
  *                  terminal_mask [S_total] globally indexed with valid ghost rows; w_scratch [K][cnt];
  *                  out = svf [cnt])
  * halo = ghost width in states (one grid row).  blocks[r] = base of rank r's block (world <= 16).
+ * overlap: boundary-first kernel -- a group of CTAs per boundary row computes and pushes that row
+ * first, so the system-scope fence and the NVLink flight overlap the interior sweep (same results).
+ * 0 = never, 1 = for the ops where it pays (soft-VI, VI), 2 = always.
  * ------------------------------------------------------------------------- */
 int    irlb200_peer_alloc(size_t bytes, void **ptr);
 int    irlb200_peer_free(void *ptr);
@@ -238,7 +241,8 @@ int    irlb200_slab_persistent(int op, int rank, int world, void *const *blocks,
                                const double *c0, const double *c1, const double *policy_in,
                                const uint8_t *terminal_mask, double *w_scratch, double discount,
                                double eps, int max_sweeps, int vi_mean, double *out, double *policy_out,
-                               int32_t *n_iter, int32_t *status, double timeout_s, void *stream);
+                               int32_t *n_iter, int32_t *status, double timeout_s, int overlap,
+                               void *stream);
 
 /* ------------------------------------------------------------------------- *
  * dense feature products on the path: reward = features . theta (maxent.py:244)

@@ -64,7 +64,7 @@ SIGNATURES = {
     "irlb200_slab_block_bytes": ([_i], ctypes.c_size_t),
     "irlb200_slab_reset": ([_vp, _vp], _i),
     "irlb200_slab_persistent": ([_i, _i, _i, ctypes.POINTER(ctypes.c_void_p), _i, _i, _i, _i, _i, _i, _vp, _vp, _vp,
-                                 _vp, _vp, _vp, _vp, _d, _d, _i, _i, _vp, _vp, _vp, _vp, _d, _vp], _i),
+                                 _vp, _vp, _vp, _vp, _d, _d, _i, _i, _vp, _vp, _vp, _vp, _d, _i, _vp], _i),
     "irlb200_backward": ([_tp, _i, _vp, _vp, _i, _i, _vp, _i, _vp], _i),
     "irlb200_soft_vi": ([_tp, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _i, _vp], _i),
     "irlb200_value_iteration": ([_tp, _i, _vp, _d, _d, _i, _i, _vp, _vp, _vp, _i, _vp], _i),

@@ -250,8 +250,11 @@ class PeerSlabGrid(SlabGrid):
     ghost-row exchange of the policy before the forward pass, and a process-group barrier
     around each launch.  CUDA only."""
 
-    def __init__(self, size, p_slip=0.2, icy=True, group=None, timeout_s=20.0):
+    def __init__(self, size, p_slip=0.2, icy=True, group=None, timeout_s=20.0, overlap=True):
         super().__init__(size, p_slip, icy, group=group, backend=CudaBackend())
+        import os
+        # boundary-first kernel: halo exchange overlaps the interior sweep (IRLB200_SLAB_OVERLAP=0/1 overrides)
+        self.overlap = int(os.environ.get("IRLB200_SLAB_OVERLAP", "1" if overlap else "0"))
         import ctypes
         E = self.backend.E
         self.E, self.ct = E, ctypes
@@ -312,7 +315,7 @@ class PeerSlabGrid(SlabGrid):
                 op, self.rank, self.world, self._blocks, self.n_states, self.lo, self.cnt, self.halo, self.A, self.K,
                 E._ptr(idx), E._ptr(p), E._ptr(c0), E._ptr(c1), E._ptr(policy_in), E._ptr(mask), E._ptr(w_scratch),
                 float(discount), float(eps), ms, int(vi_mean), E._ptr(out), E._ptr(policy_out), E._ptr(n_iter),
-                E._ptr(status), self.timeout_s, E._stream()))
+                E._ptr(status), self.timeout_s, int(self.overlap), E._stream()))
         torch.cuda.synchronize()
         self.last_n_iter, self.last_status = int(n_iter.item()), int(status.item())
         if self.last_status == ST_ABORTED:
