@@ -483,14 +483,17 @@ def expected_svf(tables, p_initial, terminal_mask_t, reward, causal=False, phi=N
 
     fused=True: one launch per batch, policy kept in shared memory (lowest latency).
     fused=False: policy pass and forward pass as two launches with their own
-    occupancy-optimal shapes (highest batch throughput).  None: fused for B < 64.
+    occupancy-optimal shapes (highest batch throughput).  None: fused for small batches of small worlds.
     Returns (svf, grad or None, policy or None)."""
     global last_info
     torch = require_cuda()
     S, A = tables.S, tables.A
     r, B = _batch2d(reward, S)
     if fused is None:
-        fused = B < 64
+        # one launch (policy kept in shared memory) wins where launch latency matters: small batches of
+        # small worlds.  Mid-size grid worlds are faster through the stencil-tiled / cluster kernels.
+        tiled = tables.stencil_n > 0 and tables.stencil_n % 4 == 0
+        fused = B < 64 and (S <= 256 or not tiled)
     # the fused kernel keeps two iterate buffers and the policy ((2 + A) * S + 34 doubles) in one CTA's
     # shared memory; irlb200_max_states_cta() quotes that limit for A = 4
     if fused and (2 + A) * S > 6 * _lib.irlb200_max_states_cta():
