@@ -904,18 +904,23 @@ static int launch_succ_cta(const SuccBatch &bt, int B, cudaStream_t st) {
             return IRLB200_OK;
         }
     }
+    // soft-VI keeps 4 exp + 1 log of temporaries live: two states per thread spill at 128 registers, and
+    // the streamed kernel (rows re-read from L1 each sweep, 64 registers) measured 1.6x faster on
+    // 1 024-state worlds, so only the other operators take the two-states-per-thread variant
+    const bool reg2 = fast && S > 512 && S <= 1024 && !force_stream && OP != kOpSoftVI;
     if (fast && S <= 512 && !force_stream) {
         auto k = succ_cta_kernel<OP, 4, 5, 1, 512, 1>;
         if (int rc = prep_smem(k, smem)) return rc;
         k<<<B, round_up32(S), smem, st>>>(bt);
-    } else if (fast && S <= 1024 && !force_stream) {
+    } else if (reg2) {
         auto k = succ_cta_kernel<OP, 4, 5, 2, 512, 1>;
         if (int rc = prep_smem(k, smem)) return rc;
         k<<<B, round_up32((S + 1) / 2), smem, st>>>(bt);
     } else if (fast) {
         auto k = succ_cta_kernel<OP, 4, 5, 0, 1024, 1>;
         if (int rc = prep_smem(k, smem)) return rc;
-        k<<<B, S < 1024 ? round_up32(S) : 1024, smem, st>>>(bt);
+        const int cap = env_int("IRLB200_STREAM_THREADS", 1024);
+        k<<<B, S < cap ? round_up32(S) : cap, smem, st>>>(bt);
     } else {
         if (A > kMaxDynA) return fail(IRLB200_EINVAL, "run-time A > 16 is not supported");
         auto k = succ_cta_kernel<OP, 0, 0, 0, 1024, 1>;
