@@ -164,6 +164,21 @@ def cpu_sparse_body(w, b):
     return time.perf_counter() - t0, n_svf
 
 
+def cpu_c_openmp(w, n_worlds=None):
+    """The same body for a slice of the batch with the plain-C restatement (oracle/c/irl_oracle.c), one
+    world per OpenMP thread on all host cores: the "optimised CPU" line (not the reference's arithmetic)."""
+    from oracle import c_port as C
+    from oracle import sparse_port as SP
+    threads = os.cpu_count() or 1
+    nw = n_worlds or 2 * threads
+    tabs = [C.ell_from_sparse(SP.icy_gridworld_sparse(w["n"], w["p_slip"][b])) for b in range(nw)]
+    sidx = np.stack([t[0] for t in tabs]); sp = np.stack([t[1] for t in tabs])
+    t0 = time.perf_counter()
+    out, n_svf = C.batch_maxent_step(sidx, sp, w["terminal"], w["p0"], w["theta0"][:nw], 1e-5)
+    dt = time.perf_counter() - t0
+    return nw / dt, threads, nw, dt, float(n_svf.mean())
+
+
 def cpu_sampled_body(w, b, n_bw=64, n_fw=256):
     """Bounded sample of the same body: the per-call dense slicing / copy of the reference
     (maxent.py:98-102,143) timed in full, n_bw backward and n_fw forward sweeps timed, then
@@ -567,6 +582,15 @@ def run_b200_arm(args):
             line["cpu_baseline"]["sparse_restatement"] = {
                 "value": 1.0 / ts, "unit": UNIT, "cores": 1,
                 "note": "scipy-CSR restatement of the same body (not the reference's dense arithmetic), %.1f s" % ts}
+            try:
+                v, thr, nw, dt, ns = cpu_c_openmp(w)
+                line["cpu_baseline"]["c_openmp_restatement"] = {
+                    "value": v, "unit": UNIT, "cores": thr,
+                    "note": "plain-C sparse restatement, one world per OpenMP thread: worlds 0..%d of the batch in "
+                            "%.1f s (%.0f forward sweeps per world); the optimised-CPU line, not the reference" % (
+                                nw - 1, dt, ns)}
+            except Exception as e:
+                line["cpu_baseline"]["c_openmp_restatement"] = {"error": repr(e)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -907,7 +907,8 @@ static int launch_succ_cta(const SuccBatch &bt, int B, cudaStream_t st) {
     // soft-VI keeps 4 exp + 1 log of temporaries live: two states per thread spill at 128 registers, and
     // the streamed kernel (rows re-read from L1 each sweep, 64 registers) measured 1.6x faster on
     // 1 024-state worlds, so only the other operators take the two-states-per-thread variant
-    const bool reg2 = fast && S > 512 && S <= 1024 && !force_stream && OP != kOpSoftVI;
+    const bool reg2 = fast && S > 512 && S <= 1024 && !force_stream &&
+                      (OP != kOpSoftVI || env_int("IRLB200_SOFTVI_REG2", 0));
     if (fast && S <= 512 && !force_stream) {
         auto k = succ_cta_kernel<OP, 4, 5, 1, 512, 1>;
         if (int rc = prep_smem(k, smem)) return rc;

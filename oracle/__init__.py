@@ -14,7 +14,10 @@ this path (`src/test_gridworld.py` pins only the zero pattern of
 itself: `tests/golden/generate_golden.py` imports the unmodified reference from
 `/root/reference/src` in the build container and writes the fixtures in
 `tests/golden/*.npz`; `tests/test_oracle_golden.py` checks every oracle
-function against every fixture.
+function against every fixture, `tests/test_oracle_c.py` does the same for the
+plain-C restatement.
 """
 
 from . import dense_port, sparse_port  # noqa: F401
+# oracle.c_port (plain-C restatement, oracle/c/irl_oracle.c) is imported on demand: it builds
+# oracle/_build/libirl_oracle.so with `make -C oracle` when missing.

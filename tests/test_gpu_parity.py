@@ -770,6 +770,14 @@ def test_c4_sampled_worlds_of_the_full_batch():
         dref, n_ref = SP.expected_svf_from_policy(mdp, p0, [Sn - 1], pa, 1e-5)
         assert nb[b, 1] == n_ref
         close(d[b], dref)
+    # 32 more worlds, evenly spaced through the batch, against the plain-C restatement (all host cores)
+    from oracle import c_port as C
+    sample = np.arange(64, B, B // 32)[:32]
+    tabs_c = [C.ell_from_sparse(SP.icy_gridworld_sparse(n, ps[b])) for b in sample]
+    out, n_c = C.batch_maxent_step(np.stack([t[0] for t in tabs_c]), np.stack([t[1] for t in tabs_c]), [Sn - 1], p0,
+                                   theta[sample])
+    assert (nb[sample, 1] == n_c).all()
+    close(d[sample], out)
 
 
 def test_c5_full_size_sweeps_against_sparse_oracle():
