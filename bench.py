@@ -268,11 +268,15 @@ def other_configs():
     import gridworld as W
     import maxent as M
     import optimizer as O
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from test_oracle_golden import load_trajectories
+    import trajectory as T
     out = {}
     g = np.load(os.path.join(ROOT, "tests", "golden", "e2e_5x5.npz"))
-    world, tjs = W.IcyGridWorld(5, 0.2), load_trajectories(g)
+    # the 200 seeded expert trajectories of main.py (fixture), as product Trajectory objects
+    tjs, off = [], 0
+    for length in g["traj_len"]:
+        tjs.append(T.Trajectory([tuple(int(v) for v in row) for row in g["traj_flat"][off:off + length]]))
+        off += length
+    world = W.IcyGridWorld(5, 0.2)
     F = W.state_features(world)
 
     class Count:
