@@ -874,12 +874,16 @@ static int launch_svf_grid5_cluster(const SvfBatch &bt, int B, int n, int ncta, 
     return IRLB200_OK;
 }
 
-// pick a cluster size for an n x n world: tile rows must split evenly, <= 256 threads per CTA
-static int cluster_size_for(int n) {
+// pick a cluster size for an n x n world: tile rows must split evenly, <= 256 threads per CTA.
+// The SMALLEST admissible cluster wins: barrier.cluster grows with the cluster (measured at 128 x 128:
+// 8 CTAs 0.95 us per sweep, 16 CTAs 1.20 us).  IRLB200_CLUSTER_SIZE forces a size; `max_c` caps it.
+static int cluster_size_for(int n, int max_c = 16) {
     if (n % 4 || n % 2) return 0;
     const int ntx = n / 4, nty = n / 2;
+    const int pref = env_int("IRLB200_CLUSTER_SIZE", 0);
     for (int c : {2, 4, 8, 16}) {
-        if (nty % c) continue;
+        if (c > max_c || nty % c) continue;
+        if (pref > 0 && c != pref) continue;
         if (ntx * (nty / c) <= 256) return c;
     }
     return 0;
@@ -1279,7 +1283,12 @@ extern "C" int irlb200_svf(const irlb200_tables *t, int B, const double *p_initi
     bt.n_iter = n_iter; bt.status = status; bt.out_stride = 1;
     if (want_cluster) {
         if (device_count_impl() <= 0) return fail(IRLB200_ECUDA, "no CUDA device");
-        const int rc = launch_svf_grid5_cluster(bt, B, t->stencil_n, cl_size, (cudaStream_t)stream);
+        int rc = launch_svf_grid5_cluster(bt, B, t->stencil_n, cl_size, (cudaStream_t)stream);
+        if (rc != IRLB200_OK && cl_size > 8) {          // 16-CTA clusters are not schedulable everywhere
+            cudaGetLastError();
+            const int c8 = cluster_size_for(t->stencil_n, 8);
+            if (c8 > 0) rc = launch_svf_grid5_cluster(bt, B, t->stencil_n, c8, (cudaStream_t)stream);
+        }
         if (rc == IRLB200_OK || mode == IRLB200_MODE_CLUSTER) return rc;
         // AUTO only: this device cannot schedule the cluster shape -> cooperative grid (same results)
         cudaGetLastError();
