@@ -835,3 +835,19 @@ def test_tiled_kernels_respect_the_sweep_guard(n, k):
     ok = np.isfinite(ref)
     assert (np.isfinite(got) == ok).all()
     np.testing.assert_allclose(got[ok], ref[ok], rtol=1e-10)
+
+
+def test_compress_dense_at_c3_size():
+    """Kernel (1) at the C3 size: the 8.59 GB dense table of IcyGridWorld(128) (built on the device)
+    compressed to tables == the directly built tables, bit for bit; K discovered = (5, 5)."""
+    import torch
+    n = 128
+    Pd = E.gridworld_dense(n, 0.2)
+    assert Pd.shape == (n * n, n * n, 4) and Pd.element_size() * Pd.numel() == 8589934592
+    a = E.compress_dense(Pd)
+    del Pd
+    torch.cuda.empty_cache()
+    b = E.gridworld_tables(n, 0.2)
+    assert a.k_discovered == (5, 5) and a.stencil_n == n
+    for x, y in ((a.succ_idx, b.succ_idx), (a.succ_p, b.succ_p), (a.pred_idx, b.pred_idx), (a.pred_p, b.pred_p)):
+        assert (x == y).all()

@@ -277,3 +277,22 @@ def test_public_signatures_match_the_reference():
     assert str(inspect.signature(O.Uniform.__init__)) == "(self, low=0.0, high=1.0)"
     assert str(inspect.signature(O.Constant.__init__)) == "(self, value=1.0)"
     assert str(inspect.signature(W.IcyGridWorld.__init__)).startswith("(self, size, p_slip=0.2")
+
+
+def test_reference_main_resolves_to_the_engine():
+    """The reference's unmodified main.py, launched through scripts/run_reference_main.py, imports the
+    ENGINE's modules and runs until the first kernel call -- which, on a box without a GPU, must be
+    the engine's loud failure (main.py:46 `S.value_iteration`).  Skipped where the reference is absent."""
+    import subprocess
+    import sys
+    ref_main = "/root/reference/src/main.py"
+    if not os.path.exists(ref_main):
+        pytest.skip("reference not present on this box")
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the run would simply succeed (covered by test_irl_5x5_like_main)")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "run_reference_main.py"), ref_main],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode != 0
+    assert "EngineError" in p.stderr and "no CPU fallback" in p.stderr
+    assert "irl-maxent_b200/solver.py" in p.stderr and "value_iteration" in p.stderr
