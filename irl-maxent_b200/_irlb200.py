@@ -296,8 +296,13 @@ def terminal_mask(terminal, S):
     """uint8 [S] mask from an index collection (device)."""
     torch = _torch()
     m = np.zeros(S, dtype=np.uint8)
-    idx = np.asarray(list(terminal), dtype=np.int64)
-    if idx.size:
+    raw = np.asarray(list(terminal))
+    if raw.size:
+        idx = raw.astype(np.int64)
+        # the forward pass needs state indices (reference: maxent.py:99 indexes the table with them); a
+        # terminal-reward ARRAY is only meaningful for the causal policy pass (maxent.py:312-317)
+        if not np.array_equal(idx, raw) or idx.min() < -S or idx.max() >= S:
+            raise EngineError("`terminal` must be a collection of state indices in [0, %d) here" % S)
         m[idx] = 1
     return torch.as_tensor(m).to(_dev())
 

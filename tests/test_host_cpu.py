@@ -296,3 +296,11 @@ def test_reference_main_resolves_to_the_engine():
     assert p.returncode != 0
     assert "EngineError" in p.stderr and "no CPU fallback" in p.stderr
     assert "irl-maxent_b200/solver.py" in p.stderr and "value_iteration" in p.stderr
+
+
+def test_terminal_must_be_indices_for_the_forward_pass():
+    """A terminal-reward array is only valid for the causal policy pass (reference: maxent.py:99 breaks too)."""
+    with pytest.raises(E.EngineError, match="state indices"):
+        E.terminal_mask(np.full(9, -1.5), 9)
+    with pytest.raises(E.EngineError, match="state indices"):
+        E.terminal_mask([3, 9], 9)
