@@ -408,6 +408,10 @@ def stream_roofline(n=2048, fw_sweeps=400, lap_sweeps=150):
         ach = bps * S * sweeps / (ms[name] / 1e3) / 1e9
         res[key] = {"sweeps": sweeps, "launch_ms": ms[name], "us_per_sweep": 1e3 * ms[name] / sweeps,
                     "bytes_per_state_sweep": bps, "achieved": ach, "frac": ach / peak}
+    # ncu --set full of the forward launch (100 sweeps, profiles/r01_svf_streamed_2048x2048.txt):
+    # dram__bytes_read 32.80 GB + dram__bytes_write 3.56 GB = 364 MB per sweep against 352 MB algorithmic
+    res["forward"]["traffic_per_sweep"] = 363.6e6 if n == 2048 else None
+    res["forward"]["algorithmic_bytes_per_sweep"] = float(SVF_BYTES_PER_STATE_SWEEP) * S
     return res
 
 
