@@ -420,8 +420,8 @@ def soft_vi(tables, phi, reward, discount, eps=1e-5, max_sweeps=None, mode=MODE_
     ph, pshared = _maybe_shared(phi, S, B)
     pol = torch.empty((B, S, A), dtype=torch.float64, device=r.device)
     val = torch.empty((B, S), dtype=torch.float64, device=r.device) if want_value else None
-    n_iter = torch.zeros(B, dtype=torch.int32, device=r.device)
-    status = torch.zeros(B, dtype=torch.int32, device=r.device)
+    n_iter = torch.empty(B, dtype=torch.int32, device=r.device)      # always written by the kernel
+    status = torch.empty(B, dtype=torch.int32, device=r.device)
     ct = tables.c_struct(_tables_shared(tables, B))
     ms = DEFAULT_MAX_SWEEPS if max_sweeps is None else int(max_sweeps)
     with _timed("soft_vi"):
@@ -438,8 +438,8 @@ def value_iteration(tables, reward, discount, eps=1e-3, max_sweeps=None, mean=Fa
     S = tables.S
     r, B = _batch2d(reward, S)
     val = torch.empty((B, S), dtype=torch.float64, device=r.device)
-    n_iter = torch.zeros(B, dtype=torch.int32, device=r.device)
-    status = torch.zeros(B, dtype=torch.int32, device=r.device)
+    n_iter = torch.empty(B, dtype=torch.int32, device=r.device)      # always written by the kernel
+    status = torch.empty(B, dtype=torch.int32, device=r.device)
     ct = tables.c_struct(_tables_shared(tables, B))
     ms = DEFAULT_MAX_SWEEPS if max_sweeps is None else int(max_sweeps)
     with _timed("value_iteration"):
@@ -469,8 +469,8 @@ def svf(tables, p_initial, terminal_mask_t, policy, eps=1e-5, max_sweeps=None, e
     if e_features is not None:
         ef, efshared = _maybe_shared(e_features, S, B)
         grad = torch.empty((B, S), dtype=torch.float64, device=pol.device)
-    n_iter = torch.zeros(B, dtype=torch.int32, device=pol.device)
-    status = torch.zeros(B, dtype=torch.int32, device=pol.device)
+    n_iter = torch.empty(B, dtype=torch.int32, device=pol.device)
+    status = torch.empty(B, dtype=torch.int32, device=pol.device)
     ct = tables.c_struct(_tables_shared(tables, B))
     ms = DEFAULT_MAX_SWEEPS if max_sweeps is None else int(max_sweeps)
     with _timed("svf"):
@@ -498,7 +498,7 @@ def expected_svf(tables, p_initial, terminal_mask_t, reward, causal=False, phi=N
         # one launch (policy kept in shared memory) wins where launch latency matters: small batches of
         # small worlds.  Mid-size grid worlds are faster through the stencil-tiled / cluster kernels.
         tiled = tables.stencil_n > 0 and tables.stencil_n % 4 == 0
-        fused = B < 64 and (S <= 256 or not tiled)
+        fused = (B < 64 and (S <= 256 or not tiled)) or (S <= 32 and A == 4 and tables.Ks == 5 and tables.Kp == 5)
     # the fused kernel keeps two iterate buffers and the policy ((2 + A) * S + 34 doubles) in one CTA's
     # shared memory; irlb200_max_states_cta() quotes that limit for A = 4
     if fused and (2 + A) * S > 6 * _lib.irlb200_max_states_cta():
@@ -533,8 +533,8 @@ def expected_svf(tables, p_initial, terminal_mask_t, reward, causal=False, phi=N
         ef, efshared = _maybe_shared(e_features, S, B)
         grad = torch.empty((B, S), dtype=torch.float64, device=r.device)
     pol = torch.empty((B, S, A), dtype=torch.float64, device=r.device) if want_policy else None
-    n_iter = torch.zeros((B, 2), dtype=torch.int32, device=r.device)
-    status = torch.zeros((B, 2), dtype=torch.int32, device=r.device)
+    n_iter = torch.empty((B, 2), dtype=torch.int32, device=r.device)
+    status = torch.empty((B, 2), dtype=torch.int32, device=r.device)
     ct = tables.c_struct(_tables_shared(tables, B))
     ms = DEFAULT_MAX_SWEEPS if max_sweeps is None else int(max_sweeps)
     with _timed("expected_svf_fused"):

@@ -145,6 +145,145 @@ __global__ void __launch_bounds__(MAXT, 1) step_cta_kernel(const StepBatch bt) {
 }
 
 // ---------------------------------------------------------------------------
+// Warp-per-world fused gradient step for tiny worlds (S <= 32, A = 4, K = 5): BASELINE configs[0..1].
+//
+// A 5x5 world is one warp of work; with one CTA per world every sweep pays a bar.red round trip
+// (~75 cycles) and two shared-memory latencies for nothing.  Here a lane IS a state: the iterate
+// lives in one register per lane, a neighbour's value is `__shfl_sync(x, idx)`, the stop rule is
+// `__any_sync` -- no barrier, no shared memory -- and a batch packs four worlds per CTA.
+// Per-state arithmetic is succ_update / the forward FMA chain, exactly as in the CTA kernels, so
+// results are bitwise identical to them.
+// ---------------------------------------------------------------------------
+template <bool CAUSAL>
+__global__ void __launch_bounds__(128) step_warp_kernel(const StepBatch bt, const int B) {
+    constexpr int A = 4, K = 5;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const size_t b = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= (size_t)B) return;                                   // whole warps leave: no block-level sync below
+    SuccArgs s = bt.s;
+    SvfArgs f = bt.f;
+    const int S = s.S;
+    const bool act = lane < S;
+    const int me = act ? lane : 0;
+    s.idx += b * bt.succ_idx_stride; s.p += b * bt.succ_p_stride; s.reward += b * S;
+    if (s.phi) s.phi += b * bt.phi_stride;
+    if (s.term) s.term += b * bt.term_stride;
+    f.idx += b * bt.pred_idx_stride; f.p += b * bt.pred_p_stride; f.p0 += b * bt.p0_stride; f.term += b * bt.term_stride;
+
+    // ---- policy pass -----------------------------------------------------------------------------
+    int ix[K];
+    double pr[A][K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        ix[j] = act ? s.idx[(size_t)j * S + me] : 0;
+#pragma unroll
+        for (int a = 0; a < A; ++a) pr[a][j] = act ? s.p[((size_t)a * K + j) * S + me] : 0.0;
+    }
+    const double r = act ? s.reward[me] : 0.0;
+    const double c0 = CAUSAL ? r : exp(r);
+    const double c1 = (CAUSAL && act) ? s.phi[me] : 0.0;
+    double x = CAUSAL ? kNegHuge : ((act && s.term[me]) ? 1.0 : 0.0);
+    double x_old = x;
+    int n_pol = 0, st_pol = IRLB200_ST_CONVERGED;
+    auto gather_update = [&](double xin, double *q) {
+        double xv[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) xv[j] = __shfl_sync(FULL, xin, ix[j]);
+        return succ_update<CAUSAL ? kOpSoftVI : kOpBackward, 4>(
+            A, K, [&](int a, int j) { return pr[a][j]; }, [&](int j) { return xv[j]; }, c0, c1, s.discount, 0, q);
+    };
+    if (CAUSAL) {
+        const int limit = s.max_sweeps > 0 ? s.max_sweeps : 0x7fffffff;
+        for (;;) {
+            const double xn = gather_update(x, nullptr);
+            const double diff = fabs(xn - x);
+            x_old = x;
+            x = xn;
+            ++n_pol;
+            const bool nan = __any_sync(FULL, act && diff != diff);
+            const bool gt = __any_sync(FULL, act && diff > s.eps);
+            if (nan) { st_pol = IRLB200_ST_NONFINITE; break; }
+            if (!gt) break;
+            if (n_pol >= limit) { st_pol = IRLB200_ST_MAXSWEEPS; break; }
+        }
+    } else {
+        double mr = fabs(r);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mr = fmax(mr, __shfl_xor_sync(FULL, mr, o));
+        const int R = backward_rescale_period(mr, A);
+        for (int t = 0; t < s.n_sweeps; ++t) {
+            x_old = x;
+            x = gather_update(x, nullptr);
+            ++n_pol;
+            if (n_pol % R == 0 && n_pol < s.n_sweeps) {
+                const double m = warp_max(act ? x : 0.0);
+                if (m > 0.0 && m < INFINITY) x = ldexp(x, -frexp_exponent(m));
+            }
+        }
+    }
+    double pol[A];
+    {
+        double q[A];
+        const double xr = gather_update(x_old, q);           // the last sweep's per-action terms, bit for bit
+#pragma unroll
+        for (int a = 0; a < A; ++a) pol[a] = CAUSAL ? exp(q[a] - x) : q[a] / xr;
+        if (!CAUSAL && n_pol == 0) {
+#pragma unroll
+            for (int a = 0; a < A; ++a) pol[a] = 0.0;
+        }
+    }
+    if (act && bt.policy_out) {
+#pragma unroll
+        for (int a = 0; a < A; ++a) bt.policy_out[(b * S + me) * A + a] = pol[a];
+    }
+
+    // ---- forward pass ------------------------------------------------------------------------------
+    int px[K];
+    double w[K];
+    const int is_term = (act && f.term[me]) ? 1 : 0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        px[j] = act ? f.idx[(size_t)j * S + me] : 0;
+        double acc = 0.0;
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            const double pa = __shfl_sync(FULL, pol[a], px[j]);                 // policy[pred_j, a]
+            const double pp = act ? __ldg(f.p + ((size_t)a * K + j) * S + me) : 0.0;
+            acc = fma(pp, pa, acc);
+        }
+        const int pterm = __shfl_sync(FULL, is_term, px[j]);
+        w[j] = (pterm || !act) ? 0.0 : acc;
+    }
+    const double p0 = act ? f.p0[me] : 0.0;
+    double d = 0.0;
+    int n_svf = 0, st_svf = IRLB200_ST_CONVERGED;
+    const int limit = f.max_sweeps > 0 ? f.max_sweeps : 0x7fffffff;
+    for (;;) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc = fma(w[j], __shfl_sync(FULL, d, px[j]), acc);
+        const double dn = p0 + acc;
+        const double diff = fabs(dn - d);
+        d = dn;
+        ++n_svf;
+        const bool nan = __any_sync(FULL, act && diff != diff);
+        const bool gt = __any_sync(FULL, act && diff > f.eps);
+        if (nan) { st_svf = IRLB200_ST_NONFINITE; break; }
+        if (!gt) break;
+        if (n_svf >= limit) { st_svf = IRLB200_ST_MAXSWEEPS; break; }
+    }
+    if (act) {
+        f.svf[b * S + me] = d;
+        if (f.grad) f.grad[b * S + me] = f.e_features[b * bt.ef_stride + me] - d;
+    }
+    if (lane == 0) {
+        if (bt.n_iter) { bt.n_iter[2 * b] = n_pol; bt.n_iter[2 * b + 1] = n_svf; }
+        if (bt.status) { bt.status[2 * b] = st_pol; bt.status[2 * b + 1] = st_svf; }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Hand-tuned forward pass for the register-resident shape (A = 4, Kp = 5).
 //
 // Same arithmetic, same order as svf_phase<CtaTopo, 4, 5, SPT> -- results are
@@ -1008,6 +1147,13 @@ static int launch_step_cta(StepBatch bt, int B, cudaStream_t st) {
     const size_t smem = cta_smem_bytes(S, A, true);
     const bool fast = is_fast_shape(A, bt.s.K) && is_fast_shape(A, bt.f.K);
     const int force_stream = env_int("IRLB200_FORCE_STREAMED", 0);
+    if (fast && S <= 32 && !force_stream && env_int("IRLB200_WARP_STEP", 1)) {
+        // tiny worlds: one warp per world, four worlds per CTA, no barriers
+        bt.f.w_scratch = nullptr;
+        step_warp_kernel<CAUSAL><<<(B + 3) / 4, 128, 0, st>>>(bt, B);
+        LAUNCH_CHECK("step_warp_kernel");
+        return IRLB200_OK;
+    }
     if (fast && S <= 512 && !force_stream) {
         bt.f.w_scratch = nullptr;
         auto k = step_cta_kernel<CAUSAL, 4, 5, 1, 512>;

@@ -184,7 +184,8 @@ def _irl_loop(p_transition, features, terminal, trajectories, optim, init, eps, 
         else:
             grad = grad[0]
         optim.step(grad)
-        delta = torch.max(torch.abs(theta_old - theta)).item()      # the one host sync per step
+        # max |theta_old - theta| (NaN propagates, which ends the loop like the reference's np.max)
+        delta = torch.linalg.vector_norm(theta_old - theta, ord=float("inf")).item()   # the one host sync per step
 
     reward = theta.clone() if identity else E.features_dot(features_d, theta)
     return _out(reward, as_t)
@@ -282,7 +283,7 @@ def irl_batch(tables, terminal, e_features, p_initial, optims, init, eps=1e-4, e
             reward, p0_a, ef_a = theta, p0, ef
         _, grad, _ = E.expected_svf(tables, p0_a, mask, reward, causal=causal, phi=phi,
                                     discount=discount if causal else 0.0, eps_lap=eps_lap, eps_svf=eps_esvf,
-                                    e_features=ef_a, fused=False)
+                                    e_features=ef_a, fused=None)
         if per_row:
             for j, b in enumerate(active):
                 optims[b].step(grad[j] if compact else grad[b])
