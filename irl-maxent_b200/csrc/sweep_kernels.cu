@@ -738,6 +738,288 @@ __global__ void __launch_bounds__(MAXT, 1) svf_grid5_cluster_kernel(const SvfBat
 }
 
 // ---------------------------------------------------------------------------
+// Push variant of the cluster forward pass (the default): no barrier.cluster in the loop.
+//
+// barrier.cluster (~430 cycles) followed by a dependent DSMEM load cost ~1 800 cycles per sweep at
+// 128 x 128 (0.95 us); the arithmetic of a sweep is ~200-350.  Here every transfer is a one-way
+// st.async -- a remote shared-memory store that decrements the transaction count of an mbarrier in
+// the DESTINATION CTA (one flight, ~320 cycles measured, scripts/ubench_cluster.cu):
+//   * halo rows: after a sweep, the threads of a CTA's first / last tile row write their boundary
+//     cells straight into the neighbouring CTA's halo buffer; the sweep itself reads local shared
+//     memory only.
+//   * stop rule: every WARP votes on its own (sampled cell first, full test when the sample finds
+//     nothing -- no CTA-wide reduction in front of the flight) and sends its vote word to the vote
+//     table of every CTA of the cluster.
+// Each CTA then waits on ONE mbarrier per sweep for (halo bytes + 4 ncta nwarps vote bytes), ORs the
+// vote table and decides -- every CTA sees the same table, so all take the same decision on the same
+// sweep, exactly where `while delta > eps` (maxent.py:108-112) stops.  A plain bar.sync orders the
+// local tile slots; it overlaps the flight.
+// (Ordinary remote stores instead of st.async are tracked by the sender's next release / bar.sync,
+// which then waits for the store's round trip, ~650 cycles; a lagged all-reduce with a one-sweep
+// rollback was measured too and lost: two mbarrier waits per sweep cost more than the flight saved.)
+//
+// Hazards: buffers and barriers are double-buffered by sweep parity.  A peer can only write parity q
+// of sweep j+2 after it has seen the votes of ALL warps of this CTA for sweep j+1, each sent after
+// that warp's last read of parity q.  Transaction bytes that land before the local
+// arrive.expect_tx are legal (the phase cannot complete before the one expected arrival).
+// Same tile arithmetic as svf_grid5_kernel: bitwise identical results, identical counts.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// false: the barrier did not complete within ~4 s (a peer CTA is gone)
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity))
+        if (clock64() - t0 > 8000000000ll) return false;
+    return true;
+}
+__device__ __forceinline__ void st_async_2f64(uint32_t raddr, double v0, double v1, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];"
+                 ::"r"(raddr), "d"(v0), "d"(v1), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void st_async_u32(uint32_t raddr, uint32_t v, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];"
+                 ::"r"(raddr), "r"(v), "r"(rbar) : "memory");
+}
+
+template <int TY, int TX, int MAXT>
+struct PushCfg {
+    using G = Grid5Cfg<TY, TX, MAXT>;
+    static constexpr int kMaxN = 128;                                     // widest grid row
+    static constexpr int kMaxCta = 16;
+    static constexpr int NWARP = MAXT / 32;
+    static_assert(kMaxCta * NWARP <= 128, "vote table: one uint4 per lane");
+    static constexpr int SLOTS = MAXT * G::PITCH * 8;                     // tile slots of one parity
+    static constexpr int HALO = 2 * kMaxN * 8;                            // [up row | down row]
+    static constexpr int VOTES = 512;                                     // uint32[cta][warp]: bad << 1 | go
+    static constexpr int STRIDE = SLOTS + HALO + VOTES;                   // bytes between the parities
+    static constexpr int MBAR = 2 * STRIDE;                               // uint64[2], by parity
+    static constexpr int BYTES = MBAR + 16;
+};
+
+// One sweep of iteration j (P = j & 1, compile time so that every shared-memory offset is an
+// immediate): decide on sweep j-1, then sweep, push, vote.  Returns kContinue or a final status.
+template <int TY, int TX, int MAXT, int P>
+__device__ __forceinline__ int svf_push_iter(unsigned char *smem, const uint32_t sbase, const uint32_t own,
+                                             const uint32_t nb_up, const uint32_t nb_dn, const uint32_t nb_lf,
+                                             const uint32_t nb_rt, const uint32_t push_up, const uint32_t push_dn,
+                                             const uint32_t bar_up, const uint32_t bar_dn, const uint32_t vote_dst,
+                                             const uint32_t vote_bar, const uint32_t expect, const int ncta,
+                                             const double (&w)[TY * TX][5], const double (&p0r)[TY * TX],
+                                             double (&cur)[TY * TX], const double eps, const int limit, int &nsw) {
+    using Cfg = PushCfg<TY, TX, MAXT>;
+    constexpr int C = TY * TX, OFF_R = P * Cfg::STRIDE, OFF_W = (P ^ 1) * Cfg::STRIDE;
+    const int j = nsw;                                                  // 0-based index of this sweep
+    // arm the barrier that collects the rows and votes of THIS sweep (its previous phase, sweep j-2,
+    // completed before this thread left iteration j-1's wait)
+    if (threadIdx.x == 0) mbar_arrive_expect_tx(sbase + Cfg::MBAR + 8 * (P ^ 1), expect);
+    if (j > 0) {
+        // rows and votes of sweep j-1
+        if (!mbar_wait(sbase + Cfg::MBAR + 8 * P, ((j - 1) >> 1) & 1)) return IRLB200_ST_ABORTED;
+        const uint4 v = *reinterpret_cast<const uint4 *>(smem + Cfg::SLOTS + Cfg::HALO + 16 * (threadIdx.x & 31) + OFF_R);
+        const unsigned all = __reduce_or_sync(0xffffffffu, v.x | v.y | v.z | v.w);
+        if (!(all & 1u)) return IRLB200_ST_CONVERGED;                   // delta <= eps everywhere
+        if (all & 2u) return IRLB200_ST_NONFINITE;
+        if (j >= limit) return IRLB200_ST_MAXSWEEPS;
+    }
+    double up[TX], dn[TX], lf[TY], rt[TY], x[C];
+#pragma unroll
+    for (int ix = 0; ix < TX; ++ix) {
+        up[ix] = *reinterpret_cast<const double *>(smem + nb_up + 8 * ((TY - 1) * TX + ix) + OFF_R);
+        dn[ix] = *reinterpret_cast<const double *>(smem + nb_dn + 8 * ix + OFF_R);
+    }
+#pragma unroll
+    for (int iy = 0; iy < TY; ++iy) {
+        lf[iy] = *reinterpret_cast<const double *>(smem + nb_lf + 8 * (iy * TX + TX - 1) + OFF_R);
+        rt[iy] = *reinterpret_cast<const double *>(smem + nb_rt + 8 * (iy * TX) + OFF_R);
+    }
+#pragma unroll
+    for (int iy = 0; iy < TY; ++iy)
+#pragma unroll
+        for (int ix = 0; ix < TX; ++ix) {
+            const int c = iy * TX + ix;
+            const double v_up = iy > 0 ? cur[c - TX] : up[ix];
+            const double v_lf = ix > 0 ? cur[c - 1] : lf[iy];
+            const double v_rt = ix < TX - 1 ? cur[c + 1] : rt[iy];
+            const double v_dn = iy < TY - 1 ? cur[c + TX] : dn[ix];
+            double acc = fma(w[c][0], v_up, 0.0);
+            acc = fma(w[c][1], v_lf, acc);
+            acc = fma(w[c][2], cur[c], acc);
+            acc = fma(w[c][3], v_rt, acc);
+            acc = fma(w[c][4], v_dn, acc);
+            x[c] = p0r[c] + acc;                                        // p_initial + sum   maxent.py:110
+        }
+    // boundary rows first: they have the longest way to go
+    if (push_up) {
+#pragma unroll
+        for (int ix = 0; ix < TX; ix += 2) st_async_2f64(push_up + 8 * ix + OFF_W, x[ix], x[ix + 1], bar_up + 8 * (P ^ 1));
+    }
+    if (push_dn) {
+#pragma unroll
+        for (int ix = 0; ix < TX; ix += 2)
+            st_async_2f64(push_dn + 8 * ix + OFF_W, x[(TY - 1) * TX + ix], x[(TY - 1) * TX + ix + 1], bar_dn + 8 * (P ^ 1));
+    }
+    nsw = j + 1;
+    // this warp's vote: sampled cell first, full test only when the sample finds nothing
+    unsigned vote = 1;
+    if (!__any_sync(0xffffffffu, !(fabs(x[0] - cur[0]) <= eps))) {
+        bool go = false;
+#pragma unroll
+        for (int c = 1; c < C; ++c) go |= !(fabs(x[c] - cur[c]) <= eps);   // |diff| > eps, or NaN
+        vote = __any_sync(0xffffffffu, go) ? 1u : 0u;
+    }
+    if ((nsw & 15) == 0) {
+        bool bad = false;
+#pragma unroll
+        for (int c = 0; c < C; ++c) bad |= (x[c] - x[c]) != 0.0;
+        if (__any_sync(0xffffffffu, bad)) vote |= 2u;
+    }
+    if ((threadIdx.x & 31) < ncta) st_async_u32(vote_dst + OFF_W, vote, vote_bar + 8 * (P ^ 1));
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        *reinterpret_cast<double *>(smem + own + 8 * c + OFF_W) = x[c];
+        cur[c] = x[c];
+    }
+    __syncthreads();                                                    // local tile slots of sweep j
+    return kContinue;
+}
+
+template <int TY, int TX, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) svf_grid5_push_kernel(const SvfBatch bt, const int n, const int R) {
+    using Cfg = PushCfg<TY, TX, MAXT>;
+    constexpr int C = TY * TX, K = 5, A = 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cgx::cluster_group cl = cgx::this_cluster();
+    const int ncta = (int)cl.num_blocks(), crank = (int)cl.block_rank();
+    const uint32_t sbase = smem_u32(smem_raw);
+
+    SvfArgs a = bt.a;
+    offset_svf(a, bt, blockIdx.x / ncta);
+    const int S = a.S, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const int ntx = n / TX;
+    const bool live = tid < ntx * R;
+    const int tx = live ? tid % ntx : 0, lty = live ? tid / ntx : 0;
+    const int gty = crank * R + lty, nty = n / TY;
+
+    double w[C][5], p0r[C], cur[C];
+    const uint32_t slot = 8u * Cfg::G::PITCH;
+    const uint32_t own = slot * tid;
+    const uint32_t nb_lf = (live && tx > 0) ? own - slot : own;
+    const uint32_t nb_rt = (live && tx < ntx - 1) ? own + slot : own;
+    // up / down neighbours: another tile of this CTA, or the halo row received from the next CTA
+    uint32_t nb_up = own, nb_dn = own, push_up = 0, push_dn = 0, bar_up = 0, bar_dn = 0;
+    if (live && lty > 0) nb_up = own - slot * ntx;
+    else if (live && gty > 0) {
+        nb_up = Cfg::SLOTS + 8u * (tx * TX) - 8u * ((TY - 1) * TX);                 // halo "up" row
+        push_up = mapa_u32(sbase + Cfg::SLOTS + 8u * (Cfg::kMaxN + tx * TX), crank - 1);   // its "down" row
+        bar_up = mapa_u32(sbase + Cfg::MBAR, crank - 1);
+    }
+    if (live && lty < R - 1) nb_dn = own + slot * ntx;
+    else if (live && gty < nty - 1) {
+        nb_dn = Cfg::SLOTS + 8u * (Cfg::kMaxN + tx * TX);
+        push_dn = mapa_u32(sbase + Cfg::SLOTS + 8u * (tx * TX), crank + 1);
+        bar_dn = mapa_u32(sbase + Cfg::MBAR, crank + 1);
+    }
+    // votes: lane l < ncta of every warp writes the warp's word into CTA l's table
+    const uint32_t vote_dst = lane < ncta ? mapa_u32(sbase + Cfg::SLOTS + Cfg::HALO + 4u * (crank * nwarp + warp), lane) : 0;
+    const uint32_t vote_bar = lane < ncta ? mapa_u32(sbase + Cfg::MBAR, lane) : 0;
+    const uint32_t expect = 4u * ncta * nwarp + (crank > 0 ? 8u * n : 0u) + (crank < ncta - 1 ? 8u * n : 0u);
+
+#pragma unroll
+    for (int iy = 0; iy < TY; ++iy)
+#pragma unroll
+        for (int ix = 0; ix < TX; ++ix) {
+            const int c = iy * TX + ix;
+            const int s = (gty * TY + iy) * n + tx * TX + ix;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) w[c][k] = 0.0;
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const int pred = a.idx[(size_t)j * S + s];
+                    double acc = 0.0;
+#pragma unroll
+                    for (int aa = 0; aa < A; ++aa)
+                        acc = fma(__ldg(a.p + ((size_t)aa * K + j) * S + s), a.policy[(size_t)pred * A + aa], acc);
+                    if (a.term[pred]) acc = 0.0;
+                    const int off = pred - s;
+                    w[c][0] += (off == -n) ? acc : 0.0;
+                    w[c][1] += (off == -1) ? acc : 0.0;
+                    w[c][2] += (off == 0) ? acc : 0.0;
+                    w[c][3] += (off == 1) ? acc : 0.0;
+                    w[c][4] += (off == n) ? acc : 0.0;
+                }
+            }
+            p0r[c] = live ? a.p0[s] : 0.0;
+            cur[c] = 0.0;
+            *reinterpret_cast<double *>(smem_raw + own + 8 * c) = 0.0;
+            *reinterpret_cast<double *>(smem_raw + own + 8 * c + Cfg::STRIDE) = 0.0;
+        }
+    for (int i = tid; i < (Cfg::HALO + Cfg::VOTES) / 8; i += blockDim.x) {
+        *reinterpret_cast<double *>(smem_raw + Cfg::SLOTS + 8 * i) = 0.0;
+        *reinterpret_cast<double *>(smem_raw + Cfg::SLOTS + 8 * i + Cfg::STRIDE) = 0.0;
+    }
+    if (tid == 0) {
+        mbar_init(sbase + Cfg::MBAR, 1);
+        mbar_init(sbase + Cfg::MBAR + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cl.sync();
+
+    const double eps = a.eps;
+    const int limit = a.max_sweeps > 0 ? a.max_sweeps : 0x7fffffff;
+    int nsw = 0, status;
+    for (;;) {
+        status = svf_push_iter<TY, TX, MAXT, 0>(smem_raw, sbase, own, nb_up, nb_dn, nb_lf, nb_rt, push_up, push_dn, bar_up,
+                                                bar_dn, vote_dst, vote_bar, expect, ncta, w, p0r, cur, eps, limit, nsw);
+        if (status != kContinue) break;
+        status = svf_push_iter<TY, TX, MAXT, 1>(smem_raw, sbase, own, nb_up, nb_dn, nb_lf, nb_rt, push_up, push_dn, bar_up,
+                                                bar_dn, vote_dst, vote_bar, expect, ncta, w, p0r, cur, eps, limit, nsw);
+        if (status != kContinue) break;
+    }
+    // Every decision is taken after ALL bytes of the sweep it judges have landed in every CTA, so nothing
+    // is in flight at this point -- except the barrier tid 0 armed for the sweep that was not run.
+
+    if (live) {
+#pragma unroll
+        for (int iy = 0; iy < TY; ++iy)
+#pragma unroll
+            for (int ix = 0; ix < TX; ++ix) {
+                const int c = iy * TX + ix;
+                const int s = (gty * TY + iy) * n + tx * TX + ix;
+                a.svf[s] = cur[c];
+                if (a.grad) a.grad[s] = a.e_features[s] - cur[c];
+            }
+    }
+    if (tid == 0 && crank == 0) {
+        const size_t wb = blockIdx.x / ncta;
+        if (bt.n_iter) bt.n_iter[wb * bt.out_stride] = nsw;
+        if (bt.status) bt.status[wb * bt.out_stride] = status;
+    }
+    cl.sync();      // keep every CTA's shared memory alive until all peers are done with it
+}
+
+// ---------------------------------------------------------------------------
 // Stencil-tiled non-causal backward pass (local_action_probabilities, maxent.py:119-159).
 //
 // All but the last of the n_sweeps partition sweeps only carry zs forward, and
@@ -1013,19 +1295,63 @@ static int launch_svf_grid5_cluster(const SvfBatch &bt, int B, int n, int ncta, 
     return IRLB200_OK;
 }
 
+// push variant (st.async + mbarrier, no barrier.cluster per sweep): the default cluster kernel
+static int launch_svf_grid5_push(const SvfBatch &bt, int B, int n, int ncta, cudaStream_t st) {
+    using Cfg = PushCfg<2, 4, 256>;
+    auto k = svf_grid5_push_kernel<2, 4, 256>;
+    const int ntx = n / 4, nty = n / 2, R = nty / ncta;
+    if (n > Cfg::kMaxN) return fail(IRLB200_ELIMIT, "cluster mode: grid row wider than 128 cells");
+    if (int rc = prep_smem(k, (size_t)Cfg::BYTES)) return rc;
+    if (ncta > 8) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(non-portable cluster)");
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(B * ncta));
+    cfg.blockDim = dim3((unsigned)round_up32(ntx * R));
+    cfg.dynamicSmemBytes = (size_t)Cfg::BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)ncta;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k, bt, n, R);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaLaunchKernelEx(svf cluster push)");
+    return IRLB200_OK;
+}
+
+static int launch_svf_cluster(const SvfBatch &bt, int B, int n, int ncta, cudaStream_t st) {
+    return env_int("IRLB200_CLUSTER_PUSH", 1) ? launch_svf_grid5_push(bt, B, n, ncta, st)
+                                              : launch_svf_grid5_cluster(bt, B, n, ncta, st);
+}
+
 // pick a cluster size for an n x n world: tile rows must split evenly, <= 256 threads per CTA.
-// The SMALLEST admissible cluster wins: barrier.cluster grows with the cluster (measured at 128 x 128:
-// 8 CTAs 0.95 us per sweep, 16 CTAs 1.20 us).  IRLB200_CLUSTER_SIZE forces a size; `max_c` caps it.
+// Push kernel (default): the flight time does not grow with the cluster, so the LARGEST portable
+// cluster that still leaves a warp of tiles per CTA wins (measured, us per sweep: 64 x 64 -- 2 CTAs
+// 0.45, 4: 0.37, 8: 0.36, 16: 0.40; 128 x 128 -- 8: 0.53, 16: 0.60); barrier.cluster kernel
+// (IRLB200_CLUSTER_PUSH=0): the barrier grows with the cluster, the SMALLEST admissible size wins
+// (128 x 128 -- 8: 0.95, 16: 1.20).  IRLB200_CLUSTER_SIZE forces a size; `max_c` caps it.
 static int cluster_size_for(int n, int max_c = 16) {
     if (n % 4 || n % 2) return 0;
     const int ntx = n / 4, nty = n / 2;
     const int pref = env_int("IRLB200_CLUSTER_SIZE", 0);
+    const bool push = env_int("IRLB200_CLUSTER_PUSH", 1) != 0;
+    int smallest = 0, best = 0;
     for (int c : {2, 4, 8, 16}) {
         if (c > max_c || nty % c) continue;
-        if (pref > 0 && c != pref) continue;
-        if (ntx * (nty / c) <= 256) return c;
+        const int threads = ntx * (nty / c);
+        if (threads > 256) continue;
+        if (pref > 0) {
+            if (c == pref) return c;
+            continue;
+        }
+        if (!smallest) smallest = c;
+        if (c <= 8 && threads >= 32) best = c;
     }
-    return 0;
+    return (push && best) ? best : smallest;
 }
 
 // ---- CTA: successor phases --------------------------------------------------
@@ -1429,11 +1755,11 @@ extern "C" int irlb200_svf(const irlb200_tables *t, int B, const double *p_initi
     bt.n_iter = n_iter; bt.status = status; bt.out_stride = 1;
     if (want_cluster) {
         if (device_count_impl() <= 0) return fail(IRLB200_ECUDA, "no CUDA device");
-        int rc = launch_svf_grid5_cluster(bt, B, t->stencil_n, cl_size, (cudaStream_t)stream);
+        int rc = launch_svf_cluster(bt, B, t->stencil_n, cl_size, (cudaStream_t)stream);
         if (rc != IRLB200_OK && cl_size > 8) {          // 16-CTA clusters are not schedulable everywhere
             cudaGetLastError();
             const int c8 = cluster_size_for(t->stencil_n, 8);
-            if (c8 > 0) rc = launch_svf_grid5_cluster(bt, B, t->stencil_n, c8, (cudaStream_t)stream);
+            if (c8 > 0) rc = launch_svf_cluster(bt, B, t->stencil_n, c8, (cudaStream_t)stream);
         }
         if (rc == IRLB200_OK || mode == IRLB200_MODE_CLUSTER) return rc;
         // AUTO only: this device cannot schedule the cluster shape -> cooperative grid (same results)

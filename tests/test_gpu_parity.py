@@ -528,9 +528,17 @@ def test_peer_slab_single_rank():
         g.close()
 
 
+@pytest.fixture(params=["push", "barrier"])
+def cluster_variant(request, monkeypatch):
+    """push: st.async + mbarrier exchange (default); barrier: barrier.cluster + DSMEM loads."""
+    monkeypatch.setenv("IRLB200_CLUSTER_PUSH", "1" if request.param == "push" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("n", [16, 64, 128])
-def test_cluster_mode_forward_pass(n):
-    """Thread-block-cluster (DSMEM) forward pass == cooperative-grid forward pass, bitwise, same count."""
+def test_cluster_mode_forward_pass(n, cluster_variant):
+    """Thread-block-cluster forward pass (both exchange variants) == cooperative-grid forward pass,
+    bitwise, same count."""
     S = n * n
     t = E.gridworld_tables(n, 0.2)
     r = np.full(S, -0.1); r[S - 1] = 1.0
@@ -556,6 +564,39 @@ def test_cluster_mode_forward_pass(n):
 def torch_stack2(pol):
     import torch
     return torch.cat([pol, pol], 0)
+
+
+@pytest.mark.parametrize("n,size", [(16, 2), (16, 4), (16, 8), (32, 16), (64, 2), (64, 16), (128, 16), (24, 4), (40, 2)])
+def test_cluster_push_every_cluster_size(n, size, monkeypatch):
+    """The push kernel at every cluster size (one tile row per CTA up to many; partly idle warps at
+    24 x 24 / 40 x 40) against the cooperative-grid kernel: bitwise, same count, also when the
+    max-sweeps guard stops it and when it stops on the first sweeps (huge eps)."""
+    monkeypatch.setenv("IRLB200_CLUSTER_PUSH", "1")
+    monkeypatch.setenv("IRLB200_CLUSTER_SIZE", str(size))
+    S = n * n
+    t = E.gridworld_tables(n, 0.2)
+    r = -np.log(4.0) + 0.05 * np.random.default_rng(n).standard_normal(S)
+    p0 = np.random.default_rng(n + 1).random(S); p0 /= p0.sum()
+    mask = E.terminal_mask([S - 1, S // 2], S)
+    pol = E.backward(t, mask, r)
+    for eps, budget in ((1e-5, 700), (1e-5, 1), (1e-5, 2), (0.5, None), (1e-3, None)):
+        d_c = E.svf(t, p0, mask, pol, eps, max_sweeps=budget, mode=E.MODE_CLUSTER)
+        n_c, st_c = counts()[0], E.last_info.stati()[0]
+        d_g = E.svf(t, p0, mask, pol, eps, max_sweeps=budget, mode=E.MODE_GRID)
+        assert counts()[0] == n_c and E.last_info.stati()[0] == st_c, (eps, budget)
+        assert (d_c == d_g).all(), (eps, budget)
+
+
+def test_cluster_push_nonfinite_stops(monkeypatch):
+    """A NaN in p_initial ends the loop with status NONFINITE in the push kernel as in the others."""
+    monkeypatch.setenv("IRLB200_CLUSTER_PUSH", "1")
+    n = 64; S = n * n
+    t = E.gridworld_tables(n, 0.2)
+    mask = E.terminal_mask([S - 1], S)
+    pol = E.backward(t, mask, np.full(S, -np.log(4.0)))
+    p0 = np.zeros(S); p0[0] = 1.0; p0[S // 3] = np.nan
+    E.svf(t, p0, mask, pol, 1e-5, max_sweeps=5000, mode=E.MODE_CLUSTER)
+    assert E.last_info.stati()[0] == E.ST_NONFINITE and counts()[0] <= 64
 
 
 # ------------------------------------------------------ randomized + edge cases ---
