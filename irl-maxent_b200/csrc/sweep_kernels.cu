@@ -1176,6 +1176,281 @@ __global__ void __launch_bounds__(MAXT, MINB) backward_grid5_kernel(const SuccBa
     }
 }
 
+// ---------------------------------------------------------------------------
+// Cluster (push) variant of the stencil-tiled backward pass: ONE world spread over a thread-block
+// cluster, for worlds too large for one CTA (BASELINE configs[2], 128 x 128: 2S = 32 768 partition
+// sweeps, 1.7 us each behind a grid barrier).  Same merged-weight sweeps, same exact last sweep and
+// same power-of-two rescale schedule as backward_grid5_kernel -- bitwise identical policies --
+// with the exchange of svf_grid5_push_kernel: boundary rows travel by st.async into the
+// neighbouring CTA's halo buffer, one mbarrier wait per sweep, no barrier.cluster in the loop.
+// The sweep count is fixed (maxent.py:154), so there are no votes; on the rescale sweeps (every R)
+// each warp sends its maximum to every CTA the same way, before the rows of that sweep are pushed.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void st_async_f64(uint32_t raddr, double v, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];"
+                 ::"r"(raddr), "d"(v), "r"(rbar) : "memory");
+}
+
+template <int TY, int TX, int MAXT>
+struct BwdPushCfg {
+    using G = Grid5Cfg<TY, TX, MAXT>;
+    static constexpr int kMaxN = 128, kMaxCta = 16, NWARP = MAXT / 32;
+    static constexpr int SLOTS = MAXT * G::PITCH * 8;
+    static constexpr int HALO = 2 * kMaxN * 8;                            // [up row | down row]
+    static constexpr int STRIDE = SLOTS + HALO;                           // bytes between the parities
+    static constexpr int MAXTAB = 2 * STRIDE;                             // double[2][kMaxCta * NWARP]: warp maxima, by rescale parity
+    static constexpr int MAXTAB_BYTES = kMaxCta * NWARP * 8;
+    static constexpr int MBAR = MAXTAB + 2 * MAXTAB_BYTES;                // uint64[2] rows by parity, uint64[2] maxima by rescale parity
+    static constexpr int SCRATCH = MBAR + 32;                             // 32 doubles + 16 doubles (cluster max of |r|)
+    static constexpr int LIN = SCRATCH + 48 * 8;                          // (R TY + 2) n doubles: zs window of the last sweep
+};
+
+template <int TY, int TX, int MAXT, int P>
+__device__ __forceinline__ bool bwd_push_iter(unsigned char *smem, const uint32_t sbase, const uint32_t own,
+                                              const uint32_t nb_up, const uint32_t nb_dn, const uint32_t nb_lf,
+                                              const uint32_t nb_rt, const uint32_t push_up, const uint32_t push_dn,
+                                              const uint32_t bar_up, const uint32_t bar_dn, const uint32_t max_dst,
+                                              const uint32_t max_bar, const uint32_t expect, const int ncta, const int nwarp,
+                                              const double (&w)[TY * TX][5], double (&cur)[TY * TX], const int t,
+                                              const bool rescale, int &n_rescale) {
+    using Cfg = BwdPushCfg<TY, TX, MAXT>;
+    constexpr int C = TY * TX, OFF_R = P * Cfg::STRIDE, OFF_W = (P ^ 1) * Cfg::STRIDE;
+    if (threadIdx.x == 0) mbar_arrive_expect_tx(sbase + Cfg::MBAR + 8 * (P ^ 1), expect);
+    if (t > 0 && !mbar_wait(sbase + Cfg::MBAR + 8 * P, ((t - 1) >> 1) & 1)) return false;
+    double up[TX], dn[TX], lf[TY], rt[TY], x[C];
+#pragma unroll
+    for (int ix = 0; ix < TX; ++ix) {
+        up[ix] = *reinterpret_cast<const double *>(smem + nb_up + 8 * ((TY - 1) * TX + ix) + OFF_R);
+        dn[ix] = *reinterpret_cast<const double *>(smem + nb_dn + 8 * ix + OFF_R);
+    }
+#pragma unroll
+    for (int iy = 0; iy < TY; ++iy) {
+        lf[iy] = *reinterpret_cast<const double *>(smem + nb_lf + 8 * (iy * TX + TX - 1) + OFF_R);
+        rt[iy] = *reinterpret_cast<const double *>(smem + nb_rt + 8 * (iy * TX) + OFF_R);
+    }
+#pragma unroll
+    for (int iy = 0; iy < TY; ++iy)
+#pragma unroll
+        for (int ix = 0; ix < TX; ++ix) {
+            const int c = iy * TX + ix;
+            const double v_up = iy > 0 ? cur[c - TX] : up[ix];
+            const double v_lf = ix > 0 ? cur[c - 1] : lf[iy];
+            const double v_rt = ix < TX - 1 ? cur[c + 1] : rt[iy];
+            const double v_dn = iy < TY - 1 ? cur[c + TX] : dn[ix];
+            double acc = fma(w[c][0], v_up, 0.0);
+            acc = fma(w[c][1], v_lf, acc);
+            acc = fma(w[c][2], cur[c], acc);
+            acc = fma(w[c][3], v_rt, acc);
+            acc = fma(w[c][4], v_dn, acc);
+            x[c] = acc;
+        }
+    if (rescale) {
+        // exact power-of-two rescale by the exponent of the cluster-wide maximum (range extension)
+        const int rp = n_rescale & 1;
+        const uint32_t mbar = sbase + Cfg::MBAR + 16 + 8 * rp;
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(mbar, 8u * ncta * nwarp);
+        double m = 0.0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) m = fmax(m, x[c]);
+        m = warp_max(m);
+        if ((threadIdx.x & 31) < ncta) st_async_f64(max_dst + Cfg::MAXTAB_BYTES * rp, m, max_bar + 8 * rp);
+        if (!mbar_wait(mbar, (n_rescale >> 1) & 1)) return false;
+        const double *tab = reinterpret_cast<const double *>(smem + Cfg::MAXTAB + Cfg::MAXTAB_BYTES * rp);
+        double gm = 0.0;
+        for (int i = threadIdx.x & 31; i < ncta * nwarp; i += 32) {
+            const double u = tab[i];
+            gm = (u > gm || u != u) ? u : gm;
+        }
+        gm = warp_max(gm);
+        if (gm > 0.0 && gm < INFINITY) {
+            const int e = frexp_exponent(gm);
+#pragma unroll
+            for (int c = 0; c < C; ++c) x[c] = ldexp(x[c], -e);
+        }
+        ++n_rescale;
+    }
+    if (push_up) {
+#pragma unroll
+        for (int ix = 0; ix < TX; ix += 2) st_async_2f64(push_up + 8 * ix + OFF_W, x[ix], x[ix + 1], bar_up + 8 * (P ^ 1));
+    }
+    if (push_dn) {
+#pragma unroll
+        for (int ix = 0; ix < TX; ix += 2)
+            st_async_2f64(push_dn + 8 * ix + OFF_W, x[(TY - 1) * TX + ix], x[(TY - 1) * TX + ix + 1], bar_dn + 8 * (P ^ 1));
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        *reinterpret_cast<double *>(smem + own + 8 * c + OFF_W) = x[c];
+        cur[c] = x[c];
+    }
+    __syncthreads();
+    return true;
+}
+
+template <int TY, int TX, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) backward_grid5_push_kernel(const SuccBatch bt, const int n, const int R) {
+    using Cfg = BwdPushCfg<TY, TX, MAXT>;
+    constexpr int C = TY * TX, K = 5, A = 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cgx::cluster_group cl = cgx::this_cluster();
+    const int ncta = (int)cl.num_blocks(), crank = (int)cl.block_rank();
+    const uint32_t sbase = smem_u32(smem_raw);
+    double *scratch = reinterpret_cast<double *>(smem_raw + Cfg::SCRATCH);
+    double *rmax_tab = scratch + 32;                                      // [ncta]: every CTA's max |r|
+    double *lin = reinterpret_cast<double *>(smem_raw + Cfg::LIN);
+
+    SuccArgs a = bt.a;
+    offset_succ(a, bt, blockIdx.x / ncta);
+    const int S = a.S, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const int ntx = n / TX;
+    const bool live = tid < ntx * R;
+    const int tx = live ? tid % ntx : 0, lty = live ? tid / ntx : 0;
+    const int gty = crank * R + lty, nty = n / TY;
+
+    double w[C][5], cur[C];
+    const uint32_t slot = 8u * Cfg::G::PITCH;
+    const uint32_t own = slot * tid;
+    const uint32_t nb_lf = (live && tx > 0) ? own - slot : own;
+    const uint32_t nb_rt = (live && tx < ntx - 1) ? own + slot : own;
+    uint32_t nb_up = own, nb_dn = own, push_up = 0, push_dn = 0, bar_up = 0, bar_dn = 0;
+    if (live && lty > 0) nb_up = own - slot * ntx;
+    else if (live && gty > 0) {
+        nb_up = Cfg::SLOTS + 8u * (tx * TX) - 8u * ((TY - 1) * TX);
+        push_up = mapa_u32(sbase + Cfg::SLOTS + 8u * (Cfg::kMaxN + tx * TX), crank - 1);
+        bar_up = mapa_u32(sbase + Cfg::MBAR, crank - 1);
+    }
+    if (live && lty < R - 1) nb_dn = own + slot * ntx;
+    else if (live && gty < nty - 1) {
+        nb_dn = Cfg::SLOTS + 8u * (Cfg::kMaxN + tx * TX);
+        push_dn = mapa_u32(sbase + Cfg::SLOTS + 8u * (tx * TX), crank + 1);
+        bar_dn = mapa_u32(sbase + Cfg::MBAR, crank + 1);
+    }
+    const uint32_t max_dst = lane < ncta ? mapa_u32(sbase + Cfg::MAXTAB + 8u * (crank * nwarp + warp), lane) : 0;
+    const uint32_t max_bar = lane < ncta ? mapa_u32(sbase + Cfg::MBAR + 16, lane) : 0;
+    const uint32_t expect = (crank > 0 ? 8u * n : 0u) + (crank < ncta - 1 ? 8u * n : 0u);
+
+    // zero the halo rows and the maxima tables before anybody writes into them
+    for (int i = tid; i < Cfg::HALO / 8; i += blockDim.x) {
+        *reinterpret_cast<double *>(smem_raw + Cfg::SLOTS + 8 * i) = 0.0;
+        *reinterpret_cast<double *>(smem_raw + Cfg::SLOTS + 8 * i + Cfg::STRIDE) = 0.0;
+    }
+    for (int i = tid; i < 2 * Cfg::MAXTAB_BYTES / 8; i += blockDim.x)
+        *reinterpret_cast<double *>(smem_raw + Cfg::MAXTAB + 8 * i) = 0.0;
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(sbase + Cfg::MBAR + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cl.sync();
+
+    double max_abs_r = 0.0;
+#pragma unroll
+    for (int iy = 0; iy < TY; ++iy)
+#pragma unroll
+        for (int ix = 0; ix < TX; ++ix) {
+            const int c = iy * TX + ix;
+            const int s = (gty * TY + iy) * n + tx * TX + ix;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) w[c][k] = 0.0;
+            double z0 = 0.0;
+            if (live) {
+                const double r = a.reward[s];
+                max_abs_r = fmax(max_abs_r, fabs(r));
+                const double er = exp(r);                                   // np.exp(reward)   :142
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const int succ = a.idx[(size_t)j * S + s];
+                    double q = 0.0;
+#pragma unroll
+                    for (int aa = 0; aa < A; ++aa) q += __ldg(a.p + ((size_t)aa * K + j) * S + s);
+                    q *= er;
+                    const int off = succ - s;
+                    w[c][0] += (off == -n) ? q : 0.0;
+                    w[c][1] += (off == -1) ? q : 0.0;
+                    w[c][2] += (off == 0) ? q : 0.0;
+                    w[c][3] += (off == 1) ? q : 0.0;
+                    w[c][4] += (off == n) ? q : 0.0;
+                }
+                z0 = a.term[s] ? 1.0 : 0.0;                                 // zs[terminal] = 1.0  :146-147
+            }
+            cur[c] = z0;
+            *reinterpret_cast<double *>(smem_raw + own + 8 * c) = z0;
+            *reinterpret_cast<double *>(smem_raw + own + 8 * c + Cfg::STRIDE) = 0.0;
+        }
+    // the start vector's boundary rows and every CTA's max |r|: plain DSMEM stores, fenced by barrier.cluster
+    if (push_up) {
+        double *dst = reinterpret_cast<double *>(cl.map_shared_rank(smem_raw, crank - 1) + Cfg::SLOTS + 8 * (Cfg::kMaxN + tx * TX));
+#pragma unroll
+        for (int ix = 0; ix < TX; ++ix) dst[ix] = cur[ix];
+    }
+    if (push_dn) {
+        double *dst = reinterpret_cast<double *>(cl.map_shared_rank(smem_raw, crank + 1) + Cfg::SLOTS + 8 * (tx * TX));
+#pragma unroll
+        for (int ix = 0; ix < TX; ++ix) dst[ix] = cur[(TY - 1) * TX + ix];
+    }
+    const double cta_max_r = block_max(max_abs_r, scratch);
+    if (tid < ncta) *cl.map_shared_rank(rmax_tab + crank, tid) = cta_max_r;
+    cl.sync();
+    double gmax_r = 0.0;
+    for (int i = 0; i < ncta; ++i) {
+        const double u = rmax_tab[i];
+        gmax_r = (u > gmax_r || u != u) ? u : gmax_r;
+    }
+    const int RP = backward_rescale_period(gmax_r, A);
+
+    // ---- n_sweeps - 1 merged-weight sweeps -------------------------------------------------
+    const int n_lin = a.n_sweeps - 1;
+    int n_rescale = 0;
+    bool ok = true;
+    for (int t = 0; t < n_lin && ok; t += 2) {
+        ok = bwd_push_iter<TY, TX, MAXT, 0>(smem_raw, sbase, own, nb_up, nb_dn, nb_lf, nb_rt, push_up, push_dn, bar_up, bar_dn,
+                                            max_dst, max_bar, expect, ncta, nwarp, w, cur, t,
+                                            (t + 1) % RP == 0 && t + 1 < n_lin, n_rescale);
+        if (!ok || t + 1 >= n_lin) break;
+        ok = bwd_push_iter<TY, TX, MAXT, 1>(smem_raw, sbase, own, nb_up, nb_dn, nb_lf, nb_rt, push_up, push_dn, bar_up, bar_dn,
+                                            max_dst, max_bar, expect, ncta, nwarp, w, cur, t + 1,
+                                            (t + 2) % RP == 0 && t + 2 < n_lin, n_rescale);
+    }
+    if (!ok) {
+        // a peer CTA never arrived (4 s timeout): make the failure loud instead of returning a half-swept policy
+        if (live)
+            for (int c = 0; c < C; ++c) {
+                const int s = (gty * TY + c / TX) * n + tx * TX + c % TX;
+                for (int aa = 0; aa < A; ++aa) a.policy[(size_t)s * A + aa] = __longlong_as_double(0x7ff8000000000000ll);
+            }
+    } else {
+        // ---- last sweep, exactly as the reference evaluates it ---------------------------------
+        const int pf = n_lin > 0 ? (n_lin & 1) : 0;                       // parity holding the final rows
+        if (n_lin > 0) ok = mbar_wait(sbase + Cfg::MBAR + 8 * pf, ((n_lin - 1) >> 1) & 1);
+        const int row0 = crank * R * TY;                                  // first grid row of this CTA; window starts one above
+        if (live) {
+#pragma unroll
+            for (int iy = 0; iy < TY; ++iy)
+#pragma unroll
+                for (int ix = 0; ix < TX; ++ix) lin[(lty * TY + iy + 1) * n + tx * TX + ix] = cur[iy * TX + ix];
+        }
+        for (int i = tid; i < n; i += blockDim.x) {
+            lin[i] = *reinterpret_cast<const double *>(smem_raw + Cfg::SLOTS + 8 * i + pf * Cfg::STRIDE);
+            lin[(R * TY + 1) * n + i] = *reinterpret_cast<const double *>(smem_raw + Cfg::SLOTS + 8 * (Cfg::kMaxN + i) + pf * Cfg::STRIDE);
+        }
+        __syncthreads();
+        if (live && a.n_sweeps > 0) {
+            const int base = (row0 - 1) * n;
+#pragma unroll 1
+            for (int c = 0; c < C; ++c) {
+                const int s = (gty * TY + c / TX) * n + tx * TX + c % TX;
+                const double er = exp(a.reward[s]);
+                double za[A];
+                const double zs = succ_update<kOpBackward, 4>(
+                    A, K, [&](int aa, int j) { return __ldg(a.p + ((size_t)aa * K + j) * S + s); },
+                    [&](int j) { return lin[__ldg(a.idx + (size_t)j * S + s) - base]; }, er, 0.0, 0.0, 0, za);
+#pragma unroll
+                for (int aa = 0; aa < A; ++aa) a.policy[(size_t)s * A + aa] = za[aa] / zs;      // :159
+            }
+        }
+    }
+    cl.sync();
+}
+
 template <int TY, int TX, int MAXT, int MINB>
 static int launch_backward_grid5(const SuccBatch &bt, int B, int n, cudaStream_t st);
 
@@ -1323,6 +1598,35 @@ static int launch_svf_grid5_push(const SvfBatch &bt, int B, int n, int ncta, cud
     return IRLB200_OK;
 }
 
+// cluster launch of the tiled backward pass (push exchange)
+static int launch_backward_grid5_push(const SuccBatch &bt, int B, int n, int ncta, cudaStream_t st) {
+    using Cfg = BwdPushCfg<2, 4, 256>;
+    auto k = backward_grid5_push_kernel<2, 4, 256>;
+    const int ntx = n / 4, nty = n / 2, R = nty / ncta;
+    if (n > Cfg::kMaxN) return fail(IRLB200_ELIMIT, "cluster mode: grid row wider than 128 cells");
+    const size_t sm = (size_t)Cfg::LIN + sizeof(double) * (size_t)(R * 2 + 2) * n;
+    if (int rc = prep_smem(k, sm)) return rc;
+    if (ncta > 8) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(non-portable cluster)");
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(B * ncta));
+    cfg.blockDim = dim3((unsigned)round_up32(ntx * R));
+    cfg.dynamicSmemBytes = sm;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)ncta;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k, bt, n, R);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaLaunchKernelEx(backward cluster push)");
+    return IRLB200_OK;
+}
+
 static int launch_svf_cluster(const SvfBatch &bt, int B, int n, int ncta, cudaStream_t st) {
     return env_int("IRLB200_CLUSTER_PUSH", 1) ? launch_svf_grid5_push(bt, B, n, ncta, st)
                                               : launch_svf_grid5_cluster(bt, B, n, ncta, st);
@@ -1334,11 +1638,11 @@ static int launch_svf_cluster(const SvfBatch &bt, int B, int n, int ncta, cudaSt
 // 0.45, 4: 0.37, 8: 0.36, 16: 0.40; 128 x 128 -- 8: 0.53, 16: 0.60); barrier.cluster kernel
 // (IRLB200_CLUSTER_PUSH=0): the barrier grows with the cluster, the SMALLEST admissible size wins
 // (128 x 128 -- 8: 0.95, 16: 1.20).  IRLB200_CLUSTER_SIZE forces a size; `max_c` caps it.
-static int cluster_size_for(int n, int max_c = 16) {
+static int cluster_size_for(int n, int max_c = 16, bool force_push = false) {
     if (n % 4 || n % 2) return 0;
     const int ntx = n / 4, nty = n / 2;
     const int pref = env_int("IRLB200_CLUSTER_SIZE", 0);
-    const bool push = env_int("IRLB200_CLUSTER_PUSH", 1) != 0;
+    const bool push = force_push || env_int("IRLB200_CLUSTER_PUSH", 1) != 0;
     int smallest = 0, best = 0;
     for (int c : {2, 4, 8, 16}) {
         if (c > max_c || nty % c) continue;
@@ -1671,12 +1975,34 @@ extern "C" int irlb200_backward(const irlb200_tables *t, int B, const double *re
                                 double *policy, int mode, void *stream) {
     if (int rc = check_tables(t, true, false)) return rc;
     if (B <= 0 || !reward || !terminal_mask || !policy || n_sweeps < 0) return fail(IRLB200_EINVAL, "backward: bad argument");
-    if (int rc = pick_mode(mode, B, t->S, t->A, false, &mode)) return rc;
+    // thread-block-cluster mode (push exchange): grid-stencil tables too large for the one-CTA tiled kernel
+    const int cl_size = (t->stencil_n > 0 && t->stencil_n * t->stencil_n == t->S && t->A == 4 && t->Ks == 5 &&
+                         t->stencil_n <= 128 && n_sweeps > 0)
+                            ? cluster_size_for(t->stencil_n, 16, true) : 0;
+    const bool want_cluster = mode == IRLB200_MODE_CLUSTER ||
+                              (mode == IRLB200_MODE_AUTO && cl_size > 0 && t->stencil_n > 64 && B <= 64 &&
+                               env_int("IRLB200_BWD_TILE", 1));
+    if (mode == IRLB200_MODE_CLUSTER && cl_size == 0)
+        return fail(IRLB200_ELIMIT, "cluster mode needs grid-stencil tables with n <= 128, n % 4 == 0");
+    if (!want_cluster)
+        if (int rc = pick_mode(mode, B, t->S, t->A, false, &mode)) return rc;
     SuccBatch bt{};
     fill_succ(bt.a, t);
     bt.a.reward = reward; bt.a.term = terminal_mask; bt.a.n_sweeps = n_sweeps; bt.a.policy = policy;
     succ_strides(bt, t);
     bt.term_stride = mask_shared ? 0 : (size_t)t->S;
+    if (want_cluster) {
+        if (device_count_impl() <= 0) return fail(IRLB200_ECUDA, "no CUDA device");
+        int rc = launch_backward_grid5_push(bt, B, t->stencil_n, cl_size, (cudaStream_t)stream);
+        if (rc != IRLB200_OK && cl_size > 8) {
+            cudaGetLastError();
+            const int c8 = cluster_size_for(t->stencil_n, 8, true);
+            if (c8 > 0) rc = launch_backward_grid5_push(bt, B, t->stencil_n, c8, (cudaStream_t)stream);
+        }
+        if (rc == IRLB200_OK || mode == IRLB200_MODE_CLUSTER) return rc;
+        cudaGetLastError();                              // AUTO only: fall back to the cooperative grid (same policy to rounding)
+        if (int rc2 = pick_mode(IRLB200_MODE_AUTO, B, t->S, t->A, false, &mode)) return rc2;
+    }
     if (mode == IRLB200_MODE_CTA) return launch_succ_cta<kOpBackward>(bt, B, (cudaStream_t)stream);
     return launch_succ_grid<kOpBackward>(bt.a, nullptr, nullptr, (cudaStream_t)stream);
 }

@@ -587,6 +587,43 @@ def test_cluster_push_every_cluster_size(n, size, monkeypatch):
         assert (d_c == d_g).all(), (eps, budget)
 
 
+@pytest.mark.parametrize("n,size", [(16, 2), (16, 8), (32, 4), (32, 16), (64, 8), (64, 2), (24, 4)])
+@pytest.mark.parametrize("regime", ["neutral", "overflow", "underflow"])
+def test_cluster_push_backward_equals_one_cta_tiled_kernel(n, size, regime, monkeypatch):
+    """Backward pass spread over a cluster (st.async row exchange, cluster-wide rescale maxima) ==
+    the one-CTA tiled kernel, bitwise, in every rescale regime and for the short sweep counts."""
+    monkeypatch.setenv("IRLB200_CLUSTER_SIZE", str(size))
+    S = n * n
+    t = E.gridworld_tables(n, 0.2)
+    rng = np.random.default_rng(7 * n + size)
+    shift = {"neutral": -np.log(4.0), "overflow": 1.5, "underflow": -9.0}[regime]
+    r = np.stack([shift + 0.05 * rng.standard_normal(S) for _ in range(2)])
+    mask = E.terminal_mask([S - 1, S // 3], S)
+    for n_sweeps in (None, 1, 2, 3, 64, 65):
+        p_c = E.backward(t, mask, r, n_sweeps=n_sweeps, mode=E.MODE_CLUSTER)
+        p_1 = E.backward(t, mask, r, n_sweeps=n_sweeps, mode=E.MODE_CTA)
+        assert p_c.shape == p_1.shape == (2, S, 4)
+        assert (p_c == p_1).all() or n_sweeps is not None and not np.isfinite(p_1.cpu().numpy()).all() and \
+            (np.isnan(p_c.cpu().numpy()) == np.isnan(p_1.cpu().numpy())).all(), (regime, n_sweeps)
+    assert np.isfinite(p_c.cpu().numpy()).all()
+
+
+def test_cluster_push_backward_128(monkeypatch):
+    """128 x 128 (BASELINE configs[2]): AUTO takes the cluster kernel; policy == per-action cooperative-grid
+    sweeps to 1e-10 and == the sparse oracle's range-extended loop."""
+    n = 128; S = n * n
+    t = E.gridworld_tables(n, 0.2)
+    r = -np.log(4.0) + 0.01 * np.random.default_rng(0).standard_normal(S)
+    mask = E.terminal_mask([S - 1], S)
+    p_auto = E.backward(t, mask, r)
+    p_cl = E.backward(t, mask, r, mode=E.MODE_CLUSTER)
+    assert (p_auto == p_cl).all()
+    p_g = E.backward(t, mask, r, mode=E.MODE_GRID)
+    close(p_cl, p_g.cpu().numpy())
+    row = p_cl[0].cpu().numpy().sum(axis=1)
+    np.testing.assert_allclose(row, 1.0, rtol=1e-12)
+
+
 def test_cluster_push_nonfinite_stops(monkeypatch):
     """A NaN in p_initial ends the loop with status NONFINITE in the push kernel as in the others."""
     monkeypatch.setenv("IRLB200_CLUSTER_PUSH", "1")
