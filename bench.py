@@ -90,12 +90,16 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t_mark = index, [], None, 0.0
+
+    def mark(self):
+        """Start of the timed region: only samples that arrive after this count."""
+        self.t_mark = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -103,7 +107,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
@@ -111,7 +115,9 @@ class ClockSampler:
         self.proc.terminate()
         time.sleep(0.05)
         sm, smax, reasons = [], None, set()
-        for r in self.rows:
+        for stamp, r in self.rows:
+            if stamp < self.t_mark:
+                continue
             try:
                 sm.append(float(r[1]))
                 smax = float(r[2])
@@ -481,12 +487,13 @@ def run_b200_arm(args):
         return svf, grad
 
     # ---- device-resident timing ---------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                                     # nvidia-smi needs a moment to come up: start it before the warm-up
     for _ in range(args.warmup):
         step_device()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     E.launch_log = []
     l0 = E.n_launches
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

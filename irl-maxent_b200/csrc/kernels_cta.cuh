@@ -1,0 +1,325 @@
+// kernels_cta.cuh -- one CTA (or one warp) per world: generic phases, fused gradient step, hand-tuned gather forward kernel.
+#pragma once
+#include "batch_args.cuh"
+
+namespace irlb200 {
+
+// ---------------------------------------------------------------------------
+// CTA kernels
+// ---------------------------------------------------------------------------
+template <int OP, int A_T, int K_T, int SPT_T, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) succ_cta_kernel(const SuccBatch bt) {
+    CtaTopo tp;
+    SuccArgs a = bt.a;
+    carve_cta(tp, a.S);
+    offset_succ(a, bt, blockIdx.x);
+    int *ni = bt.n_iter ? bt.n_iter + (size_t)blockIdx.x * bt.out_stride : nullptr;
+    int *st = bt.status ? bt.status + (size_t)blockIdx.x * bt.out_stride : nullptr;
+    succ_phase<CtaTopo, OP, A_T, K_T, SPT_T>(tp, a, ni, st);
+}
+
+template <int A_T, int K_T, int SPT_T, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) svf_cta_kernel(const SvfBatch bt) {
+    CtaTopo tp;
+    SvfArgs a = bt.a;
+    carve_cta(tp, a.S);
+    offset_svf(a, bt, blockIdx.x);
+    int *ni = bt.n_iter ? bt.n_iter + (size_t)blockIdx.x * bt.out_stride : nullptr;
+    int *st = bt.status ? bt.status + (size_t)blockIdx.x * bt.out_stride : nullptr;
+    svf_phase<CtaTopo, A_T, K_T, SPT_T>(tp, a, ni, st);
+}
+
+template <bool CAUSAL, int A_T, int K_T, int SPT_T, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) step_cta_kernel(const StepBatch bt) {
+    CtaTopo tp;
+    SuccArgs s = bt.s;
+    SvfArgs f = bt.f;
+    double *pol = carve_cta(tp, s.S);
+    const size_t b = blockIdx.x, S = s.S, A = s.A;
+    s.idx += b * bt.succ_idx_stride;
+    s.p += b * bt.succ_p_stride;
+    s.reward += b * S;
+    if (s.phi) s.phi += b * bt.phi_stride;
+    if (s.term) s.term += b * bt.term_stride;
+    s.policy = pol;
+    s.policy2 = bt.policy_out ? bt.policy_out + b * S * A : nullptr;
+    s.value = nullptr;
+    f.idx += b * bt.pred_idx_stride;
+    f.p += b * bt.pred_p_stride;
+    f.p0 += b * bt.p0_stride;
+    f.term += b * bt.term_stride;
+    f.policy = pol;
+    if (f.w_scratch) f.w_scratch += b * S * (size_t)f.K;
+    f.svf += b * S;
+    if (f.grad) {
+        f.grad += b * S;
+        f.e_features += b * bt.ef_stride;
+    }
+    int *ni = bt.n_iter ? bt.n_iter + 2 * b : nullptr;
+    int *st = bt.status ? bt.status + 2 * b : nullptr;
+    succ_phase<CtaTopo, CAUSAL ? kOpSoftVI : kOpBackward, A_T, K_T, SPT_T>(tp, s, ni, st);
+    svf_phase<CtaTopo, A_T, K_T, SPT_T>(tp, f, ni ? ni + 1 : nullptr, st ? st + 1 : nullptr);
+}
+
+// ---------------------------------------------------------------------------
+// Warp-per-world fused gradient step for tiny worlds (S <= 32, A = 4, K = 5): BASELINE configs[0..1].
+//
+// A 5x5 world is one warp of work; with one CTA per world every sweep pays a bar.red round trip
+// (~75 cycles) and two shared-memory latencies for nothing.  Here a lane IS a state: the iterate
+// lives in one register per lane, a neighbour's value is `__shfl_sync(x, idx)`, the stop rule is
+// `__any_sync` -- no barrier, no shared memory -- and a batch packs four worlds per CTA.
+// Per-state arithmetic is succ_update / the forward FMA chain, exactly as in the CTA kernels, so
+// results are bitwise identical to them.
+// ---------------------------------------------------------------------------
+template <bool CAUSAL>
+__global__ void __launch_bounds__(128) step_warp_kernel(const StepBatch bt, const int B) {
+    constexpr int A = 4, K = 5;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const size_t b = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= (size_t)B) return;                                   // whole warps leave: no block-level sync below
+    SuccArgs s = bt.s;
+    SvfArgs f = bt.f;
+    const int S = s.S;
+    const bool act = lane < S;
+    const int me = act ? lane : 0;
+    s.idx += b * bt.succ_idx_stride; s.p += b * bt.succ_p_stride; s.reward += b * S;
+    if (s.phi) s.phi += b * bt.phi_stride;
+    if (s.term) s.term += b * bt.term_stride;
+    f.idx += b * bt.pred_idx_stride; f.p += b * bt.pred_p_stride; f.p0 += b * bt.p0_stride; f.term += b * bt.term_stride;
+
+    // ---- policy pass -----------------------------------------------------------------------------
+    int ix[K];
+    double pr[A][K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        ix[j] = act ? s.idx[(size_t)j * S + me] : 0;
+#pragma unroll
+        for (int a = 0; a < A; ++a) pr[a][j] = act ? s.p[((size_t)a * K + j) * S + me] : 0.0;
+    }
+    const double r = act ? s.reward[me] : 0.0;
+    const double c0 = CAUSAL ? r : exp(r);
+    const double c1 = (CAUSAL && act) ? s.phi[me] : 0.0;
+    double x = CAUSAL ? kNegHuge : ((act && s.term[me]) ? 1.0 : 0.0);
+    double x_old = x;
+    int n_pol = 0, st_pol = IRLB200_ST_CONVERGED;
+    auto gather_update = [&](double xin, double *q) {
+        double xv[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) xv[j] = __shfl_sync(FULL, xin, ix[j]);
+        return succ_update<CAUSAL ? kOpSoftVI : kOpBackward, 4>(
+            A, K, [&](int a, int j) { return pr[a][j]; }, [&](int j) { return xv[j]; }, c0, c1, s.discount, 0, q);
+    };
+    if (CAUSAL) {
+        const int limit = s.max_sweeps > 0 ? s.max_sweeps : 0x7fffffff;
+        for (;;) {
+            const double xn = gather_update(x, nullptr);
+            const double diff = fabs(xn - x);
+            x_old = x;
+            x = xn;
+            ++n_pol;
+            const bool nan = __any_sync(FULL, act && diff != diff);
+            const bool gt = __any_sync(FULL, act && diff > s.eps);
+            if (nan) { st_pol = IRLB200_ST_NONFINITE; break; }
+            if (!gt) break;
+            if (n_pol >= limit) { st_pol = IRLB200_ST_MAXSWEEPS; break; }
+        }
+    } else {
+        double mr = fabs(r);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mr = fmax(mr, __shfl_xor_sync(FULL, mr, o));
+        const int R = backward_rescale_period(mr, A);
+        for (int t = 0; t < s.n_sweeps; ++t) {
+            x_old = x;
+            x = gather_update(x, nullptr);
+            ++n_pol;
+            if (n_pol % R == 0 && n_pol < s.n_sweeps) {
+                const double m = warp_max(act ? x : 0.0);
+                if (m > 0.0 && m < INFINITY) x = ldexp(x, -frexp_exponent(m));
+            }
+        }
+    }
+    double pol[A];
+    {
+        double q[A];
+        const double xr = gather_update(x_old, q);           // the last sweep's per-action terms, bit for bit
+#pragma unroll
+        for (int a = 0; a < A; ++a) pol[a] = CAUSAL ? exp(q[a] - x) : q[a] / xr;
+        if (!CAUSAL && n_pol == 0) {
+#pragma unroll
+            for (int a = 0; a < A; ++a) pol[a] = 0.0;
+        }
+    }
+    if (act && bt.policy_out) {
+#pragma unroll
+        for (int a = 0; a < A; ++a) bt.policy_out[(b * S + me) * A + a] = pol[a];
+    }
+
+    // ---- forward pass ------------------------------------------------------------------------------
+    int px[K];
+    double w[K];
+    const int is_term = (act && f.term[me]) ? 1 : 0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        px[j] = act ? f.idx[(size_t)j * S + me] : 0;
+        double acc = 0.0;
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            const double pa = __shfl_sync(FULL, pol[a], px[j]);                 // policy[pred_j, a]
+            const double pp = act ? __ldg(f.p + ((size_t)a * K + j) * S + me) : 0.0;
+            acc = fma(pp, pa, acc);
+        }
+        const int pterm = __shfl_sync(FULL, is_term, px[j]);
+        w[j] = (pterm || !act) ? 0.0 : acc;
+    }
+    const double p0 = act ? f.p0[me] : 0.0;
+    double d = 0.0;
+    int n_svf = 0, st_svf = IRLB200_ST_CONVERGED;
+    const int limit = f.max_sweeps > 0 ? f.max_sweeps : 0x7fffffff;
+    for (;;) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc = fma(w[j], __shfl_sync(FULL, d, px[j]), acc);
+        const double dn = p0 + acc;
+        const double diff = fabs(dn - d);
+        d = dn;
+        ++n_svf;
+        const bool nan = __any_sync(FULL, act && diff != diff);
+        const bool gt = __any_sync(FULL, act && diff > f.eps);
+        if (nan) { st_svf = IRLB200_ST_NONFINITE; break; }
+        if (!gt) break;
+        if (n_svf >= limit) { st_svf = IRLB200_ST_MAXSWEEPS; break; }
+    }
+    if (act) {
+        f.svf[b * S + me] = d;
+        if (f.grad) f.grad[b * S + me] = f.e_features[b * bt.ef_stride + me] - d;
+    }
+    if (lane == 0) {
+        if (bt.n_iter) { bt.n_iter[2 * b] = n_pol; bt.n_iter[2 * b + 1] = n_svf; }
+        if (bt.status) { bt.status[2 * b] = st_pol; bt.status[2 * b + 1] = st_svf; }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Hand-tuned forward pass for the register-resident shape (A = 4, Kp = 5).
+//
+// Same arithmetic, same order as svf_phase<CtaTopo, 4, 5, SPT> -- results are
+// bit-identical -- but the sweep body is stripped to what the FP64 pipe and the
+// issue slots must do:
+//   * the two iterate buffers sit STRIDE bytes apart (compile-time), the five
+//     gather addresses of every owned state are precomputed 32-bit shared
+//     addresses, so a sweep is 5 x (LDS.64 [addr + imm]; DFMA) per state with
+//     no address arithmetic at all;
+//   * states beyond S are padded with zero weights instead of predicated out;
+//   * the stop rule is one DSETP per state accumulated in a predicate
+//     (`!(|diff| <= eps)`, true for "greater" and for NaN) and one bar.red.or per
+//     sweep; whether a surviving vote came from a non-finite iterate is checked
+//     every 16 sweeps (such an iterate is sticky, so the loop ends within 16
+//     sweeps of the reference's NaN exit; convergent runs stop on exactly the
+//     reference's sweep).
+// ---------------------------------------------------------------------------
+// One sweep of the hand-tuned forward kernel: all gathers first, then SPT independent
+// DFMA chains (the compiler interleaves them, hiding the 8-cycle DFMA latency), then the
+// stores and the stop-rule predicates.  OFF_R / OFF_W select the iterate buffers.
+template <int SPT, int OFF_R, int OFF_W>
+__device__ __forceinline__ bool svf_fast_sweep(unsigned char *smem, const uint32_t (&ad)[SPT][5],
+                                               const uint32_t (&own)[SPT], const double (&w)[SPT][5],
+                                               const double (&p0r)[SPT], double (&cur)[SPT], double eps) {
+    double v[SPT][5], x[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) v[k][j] = *reinterpret_cast<const double *>(smem + ad[k][j] + OFF_R);
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+        double acc = fma(w[k][0], v[k][0], 0.0);
+        acc = fma(w[k][1], v[k][1], acc);
+        acc = fma(w[k][2], v[k][2], acc);
+        acc = fma(w[k][3], v[k][3], acc);
+        acc = fma(w[k][4], v[k][4], acc);
+        x[k] = p0r[k] + acc;                                            // p_initial + sum   maxent.py:110
+    }
+    bool go = false;
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+        *reinterpret_cast<double *>(smem + own[k] + OFF_W) = x[k];
+        go |= !(fabs(x[k] - cur[k]) <= eps);                            // |diff| > eps, or NaN
+        cur[k] = x[k];
+    }
+    return go;
+}
+
+template <int SPT, int STRIDE, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) svf_cta_fast_kernel(const SvfBatch bt) {
+    constexpr int K = 5, A = 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int *flag = reinterpret_cast<int *>(smem_raw + 2 * STRIDE);
+
+    SvfArgs a = bt.a;
+    offset_svf(a, bt, blockIdx.x);
+    const int S = a.S, T = blockDim.x, tid = threadIdx.x;
+
+    double w[SPT][K], p0r[SPT], cur[SPT];
+    uint32_t ad[SPT][K], own[SPT];          // byte offsets into the first iterate buffer
+
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+        const int s = tid + k * T;
+        const bool act = s < S;
+        own[k] = 8u * (uint32_t)s;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int pred = act ? a.idx[(size_t)j * S + s] : s;
+            double acc = 0.0;
+            if (act) {
+#pragma unroll
+                for (int aa = 0; aa < A; ++aa)
+                    acc = fma(__ldg(a.p + ((size_t)aa * K + j) * S + s), a.policy[(size_t)pred * A + aa], acc);
+                if (a.term[pred]) acc = 0.0;
+            }
+            w[k][j] = acc;
+            ad[k][j] = 8u * (uint32_t)pred;
+        }
+        p0r[k] = act ? a.p0[s] : 0.0;
+        cur[k] = 0.0;
+        *reinterpret_cast<double *>(smem_raw + own[k]) = 0.0;
+        *reinterpret_cast<double *>(smem_raw + own[k] + STRIDE) = 0.0;
+    }
+    if (tid == 0) *flag = 0;
+    __syncthreads();
+
+    const double eps = a.eps;
+    const int limit = a.max_sweeps > 0 ? a.max_sweeps : 0x7fffffff;
+    int n = 0, status = IRLB200_ST_CONVERGED;
+    for (;;) {
+        const bool go = (n & 1) ? svf_fast_sweep<SPT, STRIDE, 0>(smem_raw, ad, own, w, p0r, cur, eps)
+                                : svf_fast_sweep<SPT, 0, STRIDE>(smem_raw, ad, own, w, p0r, cur, eps);
+        ++n;
+        if (!__syncthreads_or(go ? 1 : 0)) break;                       // delta <= eps: converged
+        if ((n & 15) == 0) {                                            // did a vote survive on NaN?
+            bool bad = false;
+#pragma unroll
+            for (int k = 0; k < SPT; ++k) bad |= (cur[k] - cur[k]) != 0.0;   // NaN or +-inf iterate
+            if (bad) *flag = 1;     // an infinite iterate makes the next diff inf - inf = NaN
+            __syncthreads();
+            if (*flag) { status = IRLB200_ST_NONFINITE; break; }
+        }
+        if (n >= limit) { status = IRLB200_ST_MAXSWEEPS; break; }
+    }
+
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+        const int s = tid + k * T;
+        if (s < S) {
+            a.svf[s] = cur[k];
+            if (a.grad) a.grad[s] = a.e_features[s] - cur[k];
+        }
+    }
+    if (tid == 0) {
+        if (bt.n_iter) bt.n_iter[(size_t)blockIdx.x * bt.out_stride] = n;
+        if (bt.status) bt.status[(size_t)blockIdx.x * bt.out_stride] = status;
+    }
+}
+
+
+}  // namespace irlb200
