@@ -253,6 +253,31 @@ int irlb200_features_dot(const double *features, int S, int F, const double *the
 int irlb200_features_grad(const double *features, int S, int F, const double *svf,
                           const double *e_features, double *grad, void *stream);
 
+/* ------------------------------------------------------------------------- *
+ * expert demonstrations on the device
+ *   replaces trajectory.generate_trajectories / generate_trajectory, trajectory.py:52-128, whose
+ *   per-step `np.random.choice` over the dense row p_transition[s, :, a] is O(S) and needs a table
+ *   that does not exist for large worlds, and folds in the statistics of maxent.py:15-60
+ *   (feature_expectation_from_trajectories for one-hot features, initial_probabilities_from_trajectories).
+ *   n_traj independent rollouts of the stochastic policy [S][A] (a deterministic policy is a one-hot
+ *   row) through the successor table of ONE world, each from a start state drawn from start_cdf [S]
+ *   (inclusive running sum of the start distribution) until a state with terminal_mask != 0 or
+ *   max_len transitions (then *n_truncated is incremented; the reference would keep going).
+ *   Counter-based generator (Philox4x32-10; key = seed, counter = (step, trajectory)): trajectory i
+ *   depends on (seed, i) only.  numpy's global Mersenne-Twister stream is NOT reproduced -- seeded
+ *   runs of the reference's own sampler are reproduced by the host-side trajectory.py of this package.
+ *   states  [n_traj][max_len+1] int32 out or NULL   (row i: lengths[i]+1 valid entries)
+ *   actions [n_traj][max_len]   int32 out or NULL
+ *   lengths [n_traj] int32 out (transitions per trajectory)
+ *   visit_counts [S] f64, start_counts [S] f64: ACCUMULATED into (zero them first), or NULL
+ *   n_truncated  [1] int32, accumulated into
+ * ------------------------------------------------------------------------- */
+int irlb200_sample_trajectories(const irlb200_tables *t, const double *policy, const double *start_cdf,
+                                const uint8_t *terminal_mask, int n_traj, int max_len, uint64_t seed,
+                                int32_t *states, int32_t *actions, int32_t *lengths,
+                                double *visit_counts, double *start_counts, int32_t *n_truncated,
+                                void *stream);
+
 #ifdef __cplusplus
 }
 #endif

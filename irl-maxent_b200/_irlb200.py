@@ -71,6 +71,7 @@ SIGNATURES = {
     "irlb200_svf": ([_tp, _i, _vp, _i, _vp, _i, _vp, _d, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp], _i),
     "irlb200_expected_svf": ([_tp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _d, _d, _d, _i,
                               _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp], _i),
+    "irlb200_sample_trajectories": ([_tp, _vp, _vp, _vp, _i, _i, ctypes.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "irlb200_features_dot": ([_vp, _i, _i, _vp, _vp, _vp], _i),
     "irlb200_features_grad": ([_vp, _i, _i, _vp, _vp, _vp, _vp], _i),
 }
@@ -544,6 +545,39 @@ def expected_svf(tables, p_initial, terminal_mask_t, reward, causal=False, phi=N
             _ptr(out), _ptr(ef), efshared, _ptr(grad), _ptr(pol), _ptr(n_iter), _ptr(status), _stream()))
     last_info = SweepInfo(n_iter, status)
     return out, grad, pol
+
+
+def sample_trajectories(tables, policy, start, terminal_mask_t, n, seed, max_len=None, store=True):
+    """Device rollouts of a stochastic policy [S, A] through the successor table of one world
+    (trajectory.py:52-128), with the visit / start-state counts of maxent.py:15-60.
+    `start`: length-S start distribution.  Returns a dict of device tensors:
+    states [n, max_len+1] / actions [n, max_len] (store=True), lengths [n], visit_counts [S],
+    start_counts [S], n_truncated (python int; reading it synchronises)."""
+    torch = require_cuda()
+    S, A = tables.S, tables.A
+    pol = to_device(policy)
+    if tuple(pol.shape) != (S, A):
+        raise EngineError("policy must have shape [S, A]")
+    sd = to_device(start)
+    if tuple(sd.shape) != (S,):
+        raise EngineError("start must be a length-S distribution")
+    cdf = torch.cumsum(sd, 0)
+    mask = to_device(terminal_mask_t, torch.uint8)
+    max_len = int(max_len) if max_len is not None else max(1000, 50 * S)
+    dev = pol.device
+    states = torch.empty((n, max_len + 1), dtype=torch.int32, device=dev) if store else None
+    actions = torch.empty((n, max_len), dtype=torch.int32, device=dev) if store else None
+    lengths = torch.empty(n, dtype=torch.int32, device=dev)
+    visits = torch.zeros(S, dtype=torch.float64, device=dev)
+    starts = torch.zeros(S, dtype=torch.float64, device=dev)
+    trunc = torch.zeros(1, dtype=torch.int32, device=dev)
+    ct = tables.c_struct(1)
+    with _timed("sample_trajectories"):
+        _check(_lib.irlb200_sample_trajectories(ctypes.byref(ct), _ptr(pol), _ptr(cdf), _ptr(mask), int(n), max_len,
+                                                ctypes.c_uint64(int(seed) & (2 ** 64 - 1)), _ptr(states), _ptr(actions),
+                                                _ptr(lengths), _ptr(visits), _ptr(starts), _ptr(trunc), _stream()))
+    return {"states": states, "actions": actions, "lengths": lengths, "visit_counts": visits,
+            "start_counts": starts, "n_truncated": int(trunc.item()), "max_len": max_len, "start_cdf": cdf}
 
 
 def features_dot(features, theta):

@@ -12,7 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libirlmaxent_b200.so")
-SOURCES = ["host_util.cu", "tables.cu", "sweep_kernels.cu", "slab_kernels.cu", "slab_persistent.cu"]
+SOURCES = ["host_util.cu", "tables.cu", "sweep_kernels.cu", "slab_kernels.cu", "slab_persistent.cu",
+           "trajectories.cu"]
 HEADERS = ["common.cuh", "topo.cuh", "phases.cuh", "host_util.h", "batch_args.cuh", "kernels_cta.cuh",
            "kernels_tiled.cuh", "kernels_cluster.cuh",
            os.path.join("..", "..", "include", "irl_maxent_b200.h")]

@@ -55,6 +55,13 @@ def feature_expectation_from_trajectories(features, trajectories):
     """Mean over trajectories of the summed feature rows of every visited state
     (reference: maxent.py:15-39).  Accumulates in visiting order, so the result is
     bit-identical with the reference's running sum.  Host side, once per irl call."""
+    if type(trajectories).__name__ == "DeviceTrajectories":
+        # visit counts were accumulated by the sampling kernel: sum_t sum_s features[s, :] = counts . features
+        counts = trajectories.visit_counts.cpu().numpy()
+        if _is_identity(features):
+            return counts / len(trajectories)                   # integer counts: bit-identical to the running sum
+        f = features.cpu().numpy() if E.is_tensor(features) else np.asarray(features)
+        return counts.dot(f) / len(trajectories)
     if type(features).__name__ == "IdentityFeatures":
         # identity rows: the running sum of one-hot rows is a visit count (exact in float64)
         fe = np.zeros(features.shape[1])
@@ -76,6 +83,8 @@ def feature_expectation_from_trajectories(features, trajectories):
 
 def initial_probabilities_from_trajectories(n_states, trajectories):
     """Empirical start-state distribution (reference: maxent.py:42-60)."""
+    if type(trajectories).__name__ == "DeviceTrajectories":
+        return trajectories.start_counts.cpu().numpy() / len(trajectories)
     p = np.zeros(n_states)
     n = 0
     for t in trajectories:

@@ -1,8 +1,11 @@
 """
 trajectory -- expert demonstrations with the interface of the reference's
-`trajectory.py` (`/root/reference/src/trajectory.py`).  Host side; draws from
-numpy's global generator in the same order as the reference, so a seeded run
-produces the same trajectories.
+`trajectory.py` (`/root/reference/src/trajectory.py`).  The reference's functions
+stay host side and draw from numpy's global generator in the same order as the
+reference, so a seeded run produces the same trajectories.
+`generate_trajectories_device` is the device path for worlds where a Python loop
+per step is too slow: one CUDA thread per trajectory,
+counter-based generator, visit statistics accumulated on the fly.
 """
 
 import numpy as np
@@ -80,3 +83,59 @@ def policy_adapter(policy):
 def stochastic_policy_adapter(policy):
     """Stochastic policy [S, A] -> sampling callable (reference: trajectory.py:150-169)."""
     return lambda state: np.random.choice([*range(policy.shape[1])], p=policy[state, :])
+
+
+class DeviceTrajectories:
+    """n rollouts held on the device (`_irlb200.sample_trajectories`).
+
+    Iterating yields host `Trajectory` objects (so everything written against the reference's
+    interface keeps working); `maxent.feature_expectation_from_trajectories` and
+    `maxent.initial_probabilities_from_trajectories` take the device visit / start counts
+    directly instead of looping over states in Python."""
+
+    def __init__(self, raw, n_states):
+        self.n_states = n_states
+        self.states, self.actions, self.lengths = raw["states"], raw["actions"], raw["lengths"]
+        self.visit_counts, self.start_counts = raw["visit_counts"], raw["start_counts"]
+        self.n_truncated, self.max_len = raw["n_truncated"], raw["max_len"]
+
+    def __len__(self):
+        return int(self.lengths.numel())
+
+    def __iter__(self):
+        if self.states is None:
+            raise ValueError("trajectories were sampled with store=False: only the statistics exist")
+        st, ac, ln = self.states.cpu().numpy(), self.actions.cpu().numpy(), self.lengths.cpu().numpy()
+        for i in range(len(ln)):
+            k = int(ln[i])
+            yield Trajectory([(int(st[i, j]), int(ac[i, j]), int(st[i, j + 1])) for j in range(k)])
+
+
+def generate_trajectories_device(n, world, policy, start, final, seed=0, max_len=None, store=True):
+    """`generate_trajectories` (reference: trajectory.py:90-128) on the device.
+
+    `world`: a world with `.tables()` / a `_irlb200.Tables` handle / a dense `p_transition`;
+    `policy`: stochastic policy array [S, A] (the array the reference wraps with
+    `stochastic_policy_adapter`) or a deterministic policy [S] of action indices
+    (`policy_adapter`); `start`: a state, a list of states (uniform) or a length-S start
+    distribution, as in the reference; `final`: terminal states.  The random stream is the
+    device generator's (see include/irl_maxent_b200.h), not numpy's."""
+    import _irlb200 as E
+    tables = world.tables() if hasattr(world, "tables") else E.as_tables(world)
+    S, A = tables.S, tables.A
+    if E.is_tensor(policy):
+        pol = policy
+        if pol.dim() == 1:
+            pol = E._torch().nn.functional.one_hot(pol.long(), A).double()
+    else:
+        pol = np.asarray(policy)
+        if pol.ndim == 1:
+            pol = np.eye(A)[pol.astype(np.int64)]
+    starts = np.atleast_1d(start)
+    if len(starts) == S:
+        dist = starts.astype(float)
+    else:
+        dist = np.zeros(S)
+        np.add.at(dist, starts.astype(np.int64), 1.0 / len(starts))
+    raw = E.sample_trajectories(tables, pol, dist, E.terminal_mask(final, S), n, seed, max_len=max_len, store=store)
+    return DeviceTrajectories(raw, S)
