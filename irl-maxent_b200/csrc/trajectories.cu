@@ -7,7 +7,7 @@
 // One thread per trajectory; a step is two inverse-cdf draws (action from the policy row, successor
 // from the ELL row) from a counter-based generator, Philox4x32-10 keyed by the seed with the
 // counter (step, trajectory): every trajectory is a pure function of (seed, index), independent of
-// launch shape -- restated in oracle/sampler_port.py and compared bit for bit in the tests.  The
+// launch shape -- restated on the CPU by the test suite and compared bit for bit.  The
 // selection rule is numpy's: normalised running sum, first entry whose cumulative value exceeds u
 // (`cdf.searchsorted(u, side='right')`), so zero-probability entries are never chosen.
 #include <stdint.h>
