@@ -52,6 +52,8 @@ SIGNATURES = {
     "irlb200_dense_count": ([_vp, _i, _i, _vp, _vp, _vp, _vp], _i),
     "irlb200_dense_fill": ([_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "irlb200_gridworld_tables": ([_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "irlb200_gridworld_tables_k": ([_i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp], _i),
+    "irlb200_gridworld_tables_range_k": ([_i, _i, _d, _i, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "irlb200_gridworld_dense": ([_i, _i, _d, _vp, _vp], _i),
     "irlb200_gridworld_tables_range": ([_i, _i, _d, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "irlb200_slab_sweep": ([_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _d, _d, _i, _vp, _vp, _vp, _vp, _vp], _i),
@@ -228,25 +230,30 @@ def compress_dense(p_transition):
     return t
 
 
-def gridworld_tables(size, p_slip=None, icy=True):
+def gridworld_tables(size, p_slip=None, icy=True, slots=5):
     """Tables of GridWorld / IcyGridWorld straight from (size, p_slip).
-    `p_slip` may be a scalar or a length-B sequence (B worlds)."""
+    `p_slip` may be a scalar or a length-B sequence (B worlds).
+    `slots`: 5 = one slot per stencil position (register-resident, tiled and cluster kernels);
+    4 = compact form for worlds that are streamed from HBM every sweep (15-22 % fewer bytes,
+    bitwise the same results)."""
     torch = require_cuda()
+    if slots not in (4, 5):
+        raise EngineError("slots must be 4 or 5")
     if icy:
         ps = np.atleast_1d(np.asarray(p_slip, dtype=np.float64))
     else:
         ps = np.zeros(1)
     B = len(ps)
-    S, A, K = size * size, 4, 5
+    S, A, K = size * size, 4, slots
     dev = _dev()
     ps_d = to_device(ps)
     succ_idx = torch.empty((B, K, S), dtype=torch.int32, device=dev)
     succ_p = torch.empty((B, A, K, S), dtype=torch.float64, device=dev)
     pred_idx = torch.empty((B, K, S), dtype=torch.int32, device=dev)
     pred_p = torch.empty((B, A, K, S), dtype=torch.float64, device=dev)
-    _check(_lib.irlb200_gridworld_tables(size, 1 if icy else 0, B, _ptr(ps_d), _ptr(succ_idx), _ptr(succ_p),
-                                         _ptr(pred_idx), _ptr(pred_p), _stream()))
-    return Tables(S, A, K, K, succ_idx, succ_p, pred_idx, pred_p, B, stencil_n=size if size >= 2 else 0)
+    _check(_lib.irlb200_gridworld_tables_k(size, 1 if icy else 0, B, _ptr(ps_d), K, _ptr(succ_idx), _ptr(succ_p),
+                                           _ptr(pred_idx), _ptr(pred_p), _stream()))
+    return Tables(S, A, K, K, succ_idx, succ_p, pred_idx, pred_p, B, stencil_n=size if (size >= 2 and K == 5) else 0)
 
 
 def gridworld_dense(size, p_slip=0.2, icy=True):

@@ -516,6 +516,7 @@ extern "C" int irlb200_slab_persistent(int op, int rank, int world, void *const 
     // before any rank launches (slab.py does it behind a process-group barrier)
     const int threads = 256;
     const bool fast = (A == 4 && K == 5);
+    const bool compact = (A == 4 && K == 4);        // 4-slot grid-world tables: fewer bytes per streamed sweep
     int nb = 0;
     void *params[6];
     cudaError_t e;
@@ -533,9 +534,9 @@ extern "C" int irlb200_slab_persistent(int op, int rank, int world, void *const 
         if (op == 1 && (!c1 || !policy_out)) return fail(IRLB200_EINVAL, "slab_persistent: soft-VI inputs");
         void *op_params[5] = {&oa, &pe, &base, &n_iter, &status};
         const void *k = nullptr;
-        if (op == 3) k = fast ? (const void *)slab_overlap_kernel<3, 4, 5> : (const void *)slab_overlap_kernel<3, 0, 0>;
-        else if (op == 1) k = fast ? (const void *)slab_overlap_kernel<kOpSoftVI, 4, 5> : (const void *)slab_overlap_kernel<kOpSoftVI, 0, 0>;
-        else k = fast ? (const void *)slab_overlap_kernel<kOpVI, 4, 5> : (const void *)slab_overlap_kernel<kOpVI, 0, 0>;
+        if (op == 3) k = fast ? (const void *)slab_overlap_kernel<3, 4, 5> : compact ? (const void *)slab_overlap_kernel<3, 4, 4> : (const void *)slab_overlap_kernel<3, 0, 0>;
+        else if (op == 1) k = fast ? (const void *)slab_overlap_kernel<kOpSoftVI, 4, 5> : compact ? (const void *)slab_overlap_kernel<kOpSoftVI, 4, 4> : (const void *)slab_overlap_kernel<kOpSoftVI, 0, 0>;
+        else k = fast ? (const void *)slab_overlap_kernel<kOpVI, 4, 5> : compact ? (const void *)slab_overlap_kernel<kOpVI, 4, 4> : (const void *)slab_overlap_kernel<kOpVI, 0, 0>;
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -559,6 +560,10 @@ extern "C" int irlb200_slab_persistent(int op, int rank, int world, void *const 
             auto k = slab_svf_kernel<4, 5>;
             if (int rc = coop_blocks(k, cnt, threads, &nb)) return rc;
             e = cudaLaunchCooperativeKernel((const void *)k, dim3(nb), dim3(threads), params, 0, st);
+        } else if (compact) {
+            auto k = slab_svf_kernel<4, 4>;
+            if (int rc = coop_blocks(k, cnt, threads, &nb)) return rc;
+            e = cudaLaunchCooperativeKernel((const void *)k, dim3(nb), dim3(threads), params, 0, st);
         } else {
             auto k = slab_svf_kernel<0, 0>;
             if (int rc = coop_blocks(k, cnt, threads, &nb)) return rc;
@@ -575,12 +580,20 @@ extern "C" int irlb200_slab_persistent(int op, int rank, int world, void *const 
             auto k = slab_succ_kernel<kOpSoftVI, 4, 5>;
             if (int rc = coop_blocks(k, cnt, threads, &nb)) return rc;
             e = cudaLaunchCooperativeKernel((const void *)k, dim3(nb), dim3(threads), params, 0, st);
+        } else if (op == 1 && compact) {
+            auto k = slab_succ_kernel<kOpSoftVI, 4, 4>;
+            if (int rc = coop_blocks(k, cnt, threads, &nb)) return rc;
+            e = cudaLaunchCooperativeKernel((const void *)k, dim3(nb), dim3(threads), params, 0, st);
         } else if (op == 1) {
             auto k = slab_succ_kernel<kOpSoftVI, 0, 0>;
             if (int rc = coop_blocks(k, cnt, threads, &nb)) return rc;
             e = cudaLaunchCooperativeKernel((const void *)k, dim3(nb), dim3(threads), params, 0, st);
         } else if (fast) {
             auto k = slab_succ_kernel<kOpVI, 4, 5>;
+            if (int rc = coop_blocks(k, cnt, threads, &nb)) return rc;
+            e = cudaLaunchCooperativeKernel((const void *)k, dim3(nb), dim3(threads), params, 0, st);
+        } else if (compact) {
+            auto k = slab_succ_kernel<kOpVI, 4, 4>;
             if (int rc = coop_blocks(k, cnt, threads, &nb)) return rc;
             e = cudaLaunchCooperativeKernel((const void *)k, dim3(nb), dim3(threads), params, 0, st);
         } else {

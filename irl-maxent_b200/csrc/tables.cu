@@ -144,11 +144,14 @@ __device__ double world_prob(int n, int icy, double p, int s_from, int s_to, int
 
 // Rows of the states [lo, lo + cnt) only (cnt == S, lo == 0: the whole world); the arrays have
 // stride cnt and hold GLOBAL neighbour indices.  p_slip_scalar is used when p_slip == nullptr.
+// K slots per state: 5 (one per stencil position, the shape of the register-resident kernels) or 4
+// (compact: a grid-world state never has more than 4 distinct successors / predecessors -- 4
+// neighbours, or 3 + itself on an edge -- which cuts the bytes the streamed kernels move by 15-22 %).
 __global__ void gridworld_tables_kernel(int n, int icy, int B, const double *__restrict__ p_slip,
-                                        double p_slip_scalar, int lo, int cnt,
+                                        double p_slip_scalar, int lo, int cnt, int K,
                                         int32_t *succ_idx, double *succ_p,
                                         int32_t *pred_idx, double *pred_p) {
-    constexpr int K = 5, A = 4;
+    constexpr int A = 4;
     const int S = cnt;                       // stride of the output arrays
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)B * S) return;
@@ -174,12 +177,12 @@ __global__ void gridworld_tables_kernel(int n, int icy, int B, const double *__r
             nzs |= ps[a] != 0.0;
             nzp |= pq[a] != 0.0;
         }
-        if (nzs) {
+        if (nzs && js < K) {
             si[(size_t)js * S + s] = t;
             for (int a = 0; a < A; ++a) sp[((size_t)a * K + js) * S + s] = ps[a];
             ++js;
         }
-        if (nzp) {
+        if (nzp && jp < K) {
             pi[(size_t)jp * S + s] = t;
             for (int a = 0; a < A; ++a) pp[((size_t)a * K + jp) * S + s] = pq[a];
             ++jp;
@@ -292,10 +295,10 @@ extern "C" int irlb200_dense_fill(const double *P, int S, int A, int Ks, int Kp,
     return IRLB200_OK;
 }
 
-extern "C" int irlb200_gridworld_tables(int size, int icy, int B, const double *p_slip,
-                                        int32_t *succ_idx, double *succ_p,
-                                        int32_t *pred_idx, double *pred_p, void *stream) {
-    if (size <= 0 || B <= 0 || (icy && !p_slip) || !succ_idx || !succ_p || !pred_idx || !pred_p)
+extern "C" int irlb200_gridworld_tables_k(int size, int icy, int B, const double *p_slip, int K,
+                                          int32_t *succ_idx, double *succ_p,
+                                          int32_t *pred_idx, double *pred_p, void *stream) {
+    if (size <= 0 || B <= 0 || (icy && !p_slip) || !succ_idx || !succ_p || !pred_idx || !pred_p || (K != 4 && K != 5))
         return fail(IRLB200_EINVAL, "gridworld_tables: bad argument");
     if ((long long)size * size > 0x7fffffffLL) return fail(IRLB200_EINVAL, "gridworld_tables: S >= 2^31");
     if (device_count_impl() <= 0) return fail(IRLB200_ECUDA, "no CUDA device");
@@ -303,23 +306,35 @@ extern "C" int irlb200_gridworld_tables(int size, int icy, int B, const double *
     const long long blocks = (total + 255) / 256;
     if (blocks > 0x7fffffffLL) return fail(IRLB200_EINVAL, "gridworld_tables: batch too large");
     gridworld_tables_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        size, icy, B, p_slip, 0.0, 0, size * size, succ_idx, succ_p, pred_idx, pred_p);
+        size, icy, B, p_slip, 0.0, 0, size * size, K, succ_idx, succ_p, pred_idx, pred_p);
     CHECK_LAUNCH("gridworld_tables_kernel");
+    return IRLB200_OK;
+}
+
+extern "C" int irlb200_gridworld_tables(int size, int icy, int B, const double *p_slip,
+                                        int32_t *succ_idx, double *succ_p,
+                                        int32_t *pred_idx, double *pred_p, void *stream) {
+    return irlb200_gridworld_tables_k(size, icy, B, p_slip, 5, succ_idx, succ_p, pred_idx, pred_p, stream);
+}
+
+extern "C" int irlb200_gridworld_tables_range_k(int size, int icy, double p_slip, int lo, int cnt, int K,
+                                                int32_t *succ_idx, double *succ_p,
+                                                int32_t *pred_idx, double *pred_p, void *stream) {
+    if (size <= 0 || cnt <= 0 || lo < 0 || (long long)lo + cnt > (long long)size * size ||
+        !succ_idx || !succ_p || !pred_idx || !pred_p || (K != 4 && K != 5))
+        return fail(IRLB200_EINVAL, "gridworld_tables_range: bad argument");
+    if ((long long)size * size > 0x7fffffffLL) return fail(IRLB200_EINVAL, "gridworld_tables_range: S >= 2^31");
+    if (device_count_impl() <= 0) return fail(IRLB200_ECUDA, "no CUDA device");
+    gridworld_tables_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        size, icy, 1, nullptr, p_slip, lo, cnt, K, succ_idx, succ_p, pred_idx, pred_p);
+    CHECK_LAUNCH("gridworld_tables_kernel<range>");
     return IRLB200_OK;
 }
 
 extern "C" int irlb200_gridworld_tables_range(int size, int icy, double p_slip, int lo, int cnt,
                                               int32_t *succ_idx, double *succ_p,
                                               int32_t *pred_idx, double *pred_p, void *stream) {
-    if (size <= 0 || cnt <= 0 || lo < 0 || (long long)lo + cnt > (long long)size * size ||
-        !succ_idx || !succ_p || !pred_idx || !pred_p)
-        return fail(IRLB200_EINVAL, "gridworld_tables_range: bad argument");
-    if ((long long)size * size > 0x7fffffffLL) return fail(IRLB200_EINVAL, "gridworld_tables_range: S >= 2^31");
-    if (device_count_impl() <= 0) return fail(IRLB200_ECUDA, "no CUDA device");
-    gridworld_tables_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        size, icy, 1, nullptr, p_slip, lo, cnt, succ_idx, succ_p, pred_idx, pred_p);
-    CHECK_LAUNCH("gridworld_tables_kernel<range>");
-    return IRLB200_OK;
+    return irlb200_gridworld_tables_range_k(size, icy, p_slip, lo, cnt, 5, succ_idx, succ_p, pred_idx, pred_p, stream);
 }
 
 extern "C" int irlb200_gridworld_dense(int size, int icy, double p_slip, double *P, void *stream) {

@@ -124,10 +124,13 @@ class GridWorld:
         return 1.0 if into_wall else 0.0
 
     def tables(self):
-        """Device-resident compressed tables, built without the dense detour."""
+        """Device-resident compressed tables, built without the dense detour.  Worlds beyond the
+        register-resident kernels (side > 128) are streamed from HBM every sweep and get the compact
+        4-slot form; results are bitwise the same."""
         if self._tables is None:
             import _irlb200 as E
-            self._tables = E.gridworld_tables(self.size, getattr(self, "p_slip", None), icy=self.icy)
+            self._tables = E.gridworld_tables(self.size, getattr(self, "p_slip", None), icy=self.icy,
+                                              slots=4 if self.size > 128 else 5)
         return self._tables
 
     def __repr__(self):

@@ -48,17 +48,17 @@ class CudaBackend:
         self.torch = E.require_cuda()
         self.device = E._dev()
 
-    def local_tables(self, size, p_slip, icy, lo, cnt):
+    def local_tables(self, size, p_slip, icy, lo, cnt, slots=4):
         E, torch = self.E, self.torch
-        K, A = 5, 4
+        K, A = slots, 4                 # slabs are streamed every sweep: the compact 4-slot form
         t = dict(A=A, K=K,
                  succ_idx=torch.empty((K, cnt), dtype=torch.int32, device=self.device),
                  succ_p=torch.empty((A, K, cnt), dtype=torch.float64, device=self.device),
                  pred_idx=torch.empty((K, cnt), dtype=torch.int32, device=self.device),
                  pred_p=torch.empty((A, K, cnt), dtype=torch.float64, device=self.device))
-        E._check(E._lib.irlb200_gridworld_tables_range(size, 1 if icy else 0, float(p_slip), lo, cnt,
-                                                       E._ptr(t["succ_idx"]), E._ptr(t["succ_p"]),
-                                                       E._ptr(t["pred_idx"]), E._ptr(t["pred_p"]), E._stream()))
+        E._check(E._lib.irlb200_gridworld_tables_range_k(size, 1 if icy else 0, float(p_slip), lo, cnt, K,
+                                                         E._ptr(t["succ_idx"]), E._ptr(t["succ_p"]),
+                                                         E._ptr(t["pred_idx"]), E._ptr(t["pred_p"]), E._stream()))
         return t
 
     def sweep(self, op, lo, cnt, A, K, idx, p, c0, c1, discount, eps, vi_mean, x_in, x_out, vote, policy):

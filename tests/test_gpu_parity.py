@@ -528,6 +528,43 @@ def test_peer_slab_single_rank():
         g.close()
 
 
+@pytest.mark.parametrize("n,streamed", [(48, "0"), (48, "1"), (200, "0"), (200, "1")])
+def test_compact_four_slot_tables_give_bitwise_the_same_results(n, streamed, monkeypatch):
+    """irlb200_gridworld_tables_k(K = 4): no entry lost (table contents equal the 5-slot tables' non-zero
+    entries), and soft-VI / VI / forward pass / backward pass on them are bitwise those of the 5-slot
+    tables in the cooperative-grid kernels (register-resident and streamed) -- the kernels that stream
+    large worlds from HBM."""
+    monkeypatch.setenv("IRLB200_FORCE_STREAMED", streamed)
+    S = n * n
+    t5, t4 = E.gridworld_tables(n, 0.2), E.gridworld_tables(n, 0.2, slots=4)
+    assert (t4.Ks, t4.Kp, t4.stencil_n) == (4, 4, 0)
+    for i5, p5, i4, p4 in ((t5.succ_idx, t5.succ_p, t4.succ_idx, t4.succ_p), (t5.pred_idx, t5.pred_p, t4.pred_idx, t4.pred_p)):
+        i5, p5, i4, p4 = (x[0].cpu().numpy() for x in (i5, p5, i4, p4))
+        assert (p5[:, 4, :] == 0).all()                          # the fifth slot is always padding
+        assert (i5[:4] == i4).all() and (p5[:, :4, :] == p4).all()
+    r = np.full(S, -0.1); r[S - 1] = 1.0
+    p0 = np.zeros(S); p0[0] = 1.0
+    mask, phi = E.terminal_mask([S - 1], S), E.terminal_phi([S - 1], S)
+    out = []
+    for t in (t5, t4):
+        pol = E.soft_vi(t, phi, r, 0.9, mode=E.MODE_GRID)
+        n_lap = counts()[0]
+        d = E.svf(t, p0, mask, pol, 1e-5, max_sweeps=3000, mode=E.MODE_GRID)
+        n_svf = counts()[0]
+        v = E.value_iteration(t, r, 0.9, 1e-4, mode=E.MODE_GRID)
+        n_vi = counts()[0]
+        pb = E.backward(t, mask, np.full(S, -np.log(4.0)), n_sweeps=200, mode=E.MODE_GRID)
+        out.append((pol, d, v, pb, n_lap, n_svf, n_vi))
+    for a, b in zip(out[0][:4], out[1][:4]):
+        # 200 backward sweeps do not reach every state of the 200 x 200 world: 0 / 0 there, in both
+        assert np.array_equal(a.cpu().numpy(), b.cpu().numpy(), equal_nan=True)
+    assert out[0][4:] == out[1][4:]
+    # the batched one-CTA kernels take the compact tables too (generic gather)
+    if n == 48:
+        d1 = E.svf(t4, p0, mask, out[1][0], 1e-5, max_sweeps=3000, mode=E.MODE_CTA)
+        assert (d1 == out[1][1]).all()
+
+
 @pytest.fixture(params=["push", "barrier"])
 def cluster_variant(request, monkeypatch):
     """push: st.async + mbarrier exchange (default); barrier: barrier.cluster + DSMEM loads."""
