@@ -450,6 +450,9 @@ def stream_roofline(n=2048, fw_sweeps=400, lap_sweeps=150):
                     "moved_bytes_per_state_sweep": moved[key], "moved_GBps": phys, "moved_frac": phys / peak}
     # ncu --set full of the forward launch with 5-slot tables (100 sweeps, profiles/r01_svf_streamed_2048x2048.txt):
     # dram__bytes_read 32.80 GB + dram__bytes_write 3.56 GB = 364 MB per sweep against 352 MB moved by design
+    # ... and with the 4-slot tables (profiles/r01_svf_streamed_2048x2048_4slot.txt): 27.62 + 3.52 GB over 100 sweeps
+    res["forward"]["traffic_per_sweep"] = 311.4e6 if n == 2048 else None
+    res["forward"]["moved_bytes_per_sweep"] = float(moved["forward"]) * S
     res["forward"]["algorithmic_bytes_per_sweep"] = float(SVF_BYTES_PER_STATE_SWEEP) * S
     del tabs
     torch.cuda.empty_cache()
