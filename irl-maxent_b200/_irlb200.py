@@ -562,6 +562,8 @@ def sample_trajectories(tables, policy, start, terminal_mask_t, n, seed, max_len
     start_counts [S], n_truncated (python int; reading it synchronises)."""
     torch = require_cuda()
     S, A = tables.S, tables.A
+    if tables.n_tables != 1:
+        raise EngineError("sample_trajectories takes the tables of one world (use tables.select(b))")
     pol = to_device(policy)
     if tuple(pol.shape) != (S, A):
         raise EngineError("policy must have shape [S, A]")

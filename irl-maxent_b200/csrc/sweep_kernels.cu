@@ -586,7 +586,7 @@ extern "C" int irlb200_backward(const irlb200_tables *t, int B, const double *re
                          t->stencil_n <= 128 && n_sweeps > 0)
                             ? cluster_size_for(t->stencil_n, 16, true) : 0;
     const bool want_cluster = mode == IRLB200_MODE_CLUSTER ||
-                              (mode == IRLB200_MODE_AUTO && cl_size > 0 && t->stencil_n > 64 && B <= 64 &&
+                              (mode == IRLB200_MODE_AUTO && cl_size > 0 && t->stencil_n > 64 &&
                                env_int("IRLB200_BWD_TILE", 1));
     if (mode == IRLB200_MODE_CLUSTER && cl_size == 0)
         return fail(IRLB200_ELIMIT, "cluster mode needs grid-stencil tables with n <= 128, n % 4 == 0");
