@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(MAXT, MINB) svf_grid5_kernel(const SvfBatch bt
 // reference does (per-action za = er * P_a.dot(zs), zs = za.sum, policy = za / zs, :155-159)
 // from the ELL rows.  Range extension: exact power-of-two rescale every R sweeps.
 // ---------------------------------------------------------------------------
-template <int TY, int TX, int MAXT, int OFF_R, int OFF_W>
+template <int TY, int TX, int MAXT, int OFF_R, int OFF_W, bool WANT_MAX>
 __device__ __forceinline__ double lin_grid5_sweep(unsigned char *smem, uint32_t own, uint32_t nb_up, uint32_t nb_dn,
                                                   uint32_t nb_lf, uint32_t nb_rt, const double (&w)[TY * TX][5],
                                                   double (&cur)[TY * TX]) {
@@ -217,7 +217,7 @@ __device__ __forceinline__ double lin_grid5_sweep(unsigned char *smem, uint32_t 
     for (int c = 0; c < TY * TX; ++c) {
         *reinterpret_cast<double *>(smem + own + 8 * c + OFF_W) = x[c];
         cur[c] = x[c];
-        m = fmax(m, x[c]);
+        if (WANT_MAX) m = fmax(m, x[c]);                  // only the rescale sweeps need the maximum
     }
     return m;
 }
@@ -284,11 +284,21 @@ __global__ void __launch_bounds__(MAXT, MINB) backward_grid5_kernel(const SuccBa
 
     // ---- n_sweeps - 1 merged-weight sweeps -------------------------------------------------
     const int n_lin = a.n_sweeps - 1;
+    int until_rescale = R;                                  // countdown instead of (t + 1) % R
     for (int t = 0; t < n_lin; ++t) {
-        const double m = (t & 1)
-            ? lin_grid5_sweep<TY, TX, MAXT, STRIDE, 0>(smem_raw, own, nb_up, nb_dn, nb_lf, nb_rt, w, cur)
-            : lin_grid5_sweep<TY, TX, MAXT, 0, STRIDE>(smem_raw, own, nb_up, nb_dn, nb_lf, nb_rt, w, cur);
-        if ((t + 1) % R == 0 && t + 1 < n_lin) {
+        const bool rescale = --until_rescale == 0 && t + 1 < n_lin;
+        if (until_rescale == 0) until_rescale = R;
+        double m = 0.0;
+        if (rescale) {
+            m = (t & 1)
+                ? lin_grid5_sweep<TY, TX, MAXT, STRIDE, 0, true>(smem_raw, own, nb_up, nb_dn, nb_lf, nb_rt, w, cur)
+                : lin_grid5_sweep<TY, TX, MAXT, 0, STRIDE, true>(smem_raw, own, nb_up, nb_dn, nb_lf, nb_rt, w, cur);
+        } else if (t & 1) {
+            lin_grid5_sweep<TY, TX, MAXT, STRIDE, 0, false>(smem_raw, own, nb_up, nb_dn, nb_lf, nb_rt, w, cur);
+        } else {
+            lin_grid5_sweep<TY, TX, MAXT, 0, STRIDE, false>(smem_raw, own, nb_up, nb_dn, nb_lf, nb_rt, w, cur);
+        }
+        if (rescale) {
             const double gm = block_max(m, scratch);           // two barriers inside
             if (gm > 0.0 && gm < INFINITY) {
                 const int e = frexp_exponent(gm);
