@@ -63,6 +63,34 @@ __device__ __forceinline__ void svf_grid5_sweep(unsigned char *smem, uint32_t ow
     for (int c = 0; c < TY * TX; ++c) *reinterpret_cast<double *>(smem + own + 8 * c + OFF_W) = x[c];
 }
 
+// One sweep src -> dst plus the stop rule.  Returns kContinue or the final status.
+template <int TY, int TX, int MAXT, int OFF_R, int OFF_W>
+__device__ __forceinline__ int svf_grid5_step(unsigned char *smem, uint32_t own, uint32_t nb_up, uint32_t nb_dn,
+                                              uint32_t nb_lf, uint32_t nb_rt, const double (&w)[TY * TX][5],
+                                              const double (&p0r)[TY * TX], const double (&src)[TY * TX],
+                                              double (&dst)[TY * TX], const double eps, const int limit, int &nsw,
+                                              int *flag) {
+    constexpr int C = TY * TX;
+    svf_grid5_sweep<TY, TX, MAXT, OFF_R, OFF_W>(smem, own, nb_up, nb_dn, nb_lf, nb_rt, w, p0r, src, dst);
+    ++nsw;
+    if (!__syncthreads_or(!(fabs(dst[0] - src[0]) <= eps) ? 1 : 0)) {
+        bool go = false;
+#pragma unroll
+        for (int c = 1; c < C; ++c) go |= !(fabs(dst[c] - src[c]) <= eps);   // |diff| > eps, or NaN
+        if (!__syncthreads_or(go ? 1 : 0)) return IRLB200_ST_CONVERGED;     // delta <= eps
+    }
+    if ((nsw & 15) == 0) {
+        bool bad = false;
+#pragma unroll
+        for (int c = 0; c < C; ++c) bad |= (dst[c] - dst[c]) != 0.0;
+        if (bad) *flag = 1;
+        __syncthreads();
+        if (*flag) return IRLB200_ST_NONFINITE;
+    }
+    if (nsw >= limit) return IRLB200_ST_MAXSWEEPS;
+    return kContinue;
+}
+
 template <int TY, int TX, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) svf_grid5_kernel(const SvfBatch bt, const int n) {
     using Cfg = Grid5Cfg<TY, TX, MAXT>;
@@ -125,31 +153,19 @@ __global__ void __launch_bounds__(MAXT, MINB) svf_grid5_kernel(const SvfBatch bt
     // vote finds nothing -- the last few hundred of ~10^4..10^5.  Stopping always needs the full test.
     const double eps = a.eps;
     const int limit = a.max_sweeps > 0 ? a.max_sweeps : 0x7fffffff;
-    int nsw = 0, status = IRLB200_ST_CONVERGED;
+    // Two sweeps per trip, ping-ponging between two register arrays (cur -> x, x -> cur): no copies and no
+    // parity branch in the loop (they were 20 of the ~100 instructions of a thread-sweep).
+    int nsw = 0, status;
+    double x[C];
     for (;;) {
-        double x[C];
-        if (nsw & 1) svf_grid5_sweep<TY, TX, MAXT, STRIDE, 0>(smem_raw, own, nb_up, nb_dn, nb_lf, nb_rt, w, p0r, cur, x);
-        else svf_grid5_sweep<TY, TX, MAXT, 0, STRIDE>(smem_raw, own, nb_up, nb_dn, nb_lf, nb_rt, w, p0r, cur, x);
-        ++nsw;
-        bool stop = false;
-        if (!__syncthreads_or(!(fabs(x[0] - cur[0]) <= eps) ? 1 : 0)) {
-            bool go = false;
+        status = svf_grid5_step<TY, TX, MAXT, 0, STRIDE>(smem_raw, own, nb_up, nb_dn, nb_lf, nb_rt, w, p0r, cur, x, eps, limit, nsw, flag);
+        if (status != kContinue) {
 #pragma unroll
-            for (int c = 1; c < C; ++c) go |= !(fabs(x[c] - cur[c]) <= eps);   // |diff| > eps, or NaN
-            stop = !__syncthreads_or(go ? 1 : 0);
+            for (int c = 0; c < C; ++c) cur[c] = x[c];
+            break;
         }
-#pragma unroll
-        for (int c = 0; c < C; ++c) cur[c] = x[c];
-        if (stop) break;                                                // delta <= eps: converged
-        if ((nsw & 15) == 0) {
-            bool bad = false;
-#pragma unroll
-            for (int c = 0; c < C; ++c) bad |= (cur[c] - cur[c]) != 0.0;
-            if (bad) *flag = 1;
-            __syncthreads();
-            if (*flag) { status = IRLB200_ST_NONFINITE; break; }
-        }
-        if (nsw >= limit) { status = IRLB200_ST_MAXSWEEPS; break; }
+        status = svf_grid5_step<TY, TX, MAXT, STRIDE, 0>(smem_raw, own, nb_up, nb_dn, nb_lf, nb_rt, w, p0r, x, cur, eps, limit, nsw, flag);
+        if (status != kContinue) break;
     }
 
     if (live) {
