@@ -557,8 +557,8 @@ def run_b200_arm(args):
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
                 "traffic": traffic,
-                "binding_resource": "on-chip: shared-memory datapath (ncu 73% of peak wavefronts at 3 worlds/SM), "
-                                    "FP64 pipe 47%, issue slots 47%; DRAM 0.9% busy",
+                "binding_resource": "on-chip: shared-memory datapath (ncu 80.6% of peak wavefronts at 3 worlds/SM), "
+                                    "FP64 pipe 51%, issue slots 42%; DRAM 0.2% busy (profiles/r01_svf_grid5_kernel.txt)",
                 "algorithmic_bytes_per_launch": svf_bytes, "launch_ms": svf_ms,
                 "share_of_step": svf_ms * args.steps / ms_total if ms_total else None,
                 "forward_sweeps_per_world_mean": float(n_fw.mean()) / B,
