@@ -56,7 +56,11 @@ extern "C" {
 /* execution modes for a single problem (batched calls always use IRLB200_MODE_CTA) */
 #define IRLB200_MODE_AUTO     0
 #define IRLB200_MODE_CTA      1   /* one CTA owns the problem: iterate in shared memory      */
-#define IRLB200_MODE_CLUSTER  2   /* one thread-block cluster owns it: iterate in DSMEM      */
+#define IRLB200_MODE_CLUSTER  2   /* one thread-block cluster (<= 16 CTAs) owns it: iterate in registers +
+                                     distributed shared memory, rows and votes exchanged by st.async into the
+                                     peers' shared memory.  Exists for irlb200_backward and irlb200_svf on 5-slot
+                                     grid-stencil tables with n <= 128, n % 4 == 0 (also batches of such worlds);
+                                     IRLB200_ELIMIT otherwise.  AUTO picks it for worlds beyond one CTA.        */
 #define IRLB200_MODE_GRID     3   /* cooperative persistent grid: iterate in L2/HBM          */
 
 int         irlb200_version(void);
