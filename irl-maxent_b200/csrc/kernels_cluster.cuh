@@ -34,22 +34,7 @@ __device__ __forceinline__ void svf_grid5_cluster_sweep(unsigned char *smem, uin
         lf[iy] = *reinterpret_cast<const double *>(smem + nb_lf + 8 * (iy * TX + TX - 1) + OFF_R);
         rt[iy] = *reinterpret_cast<const double *>(smem + nb_rt + 8 * (iy * TX) + OFF_R);
     }
-#pragma unroll
-    for (int iy = 0; iy < TY; ++iy)
-#pragma unroll
-        for (int ix = 0; ix < TX; ++ix) {
-            const int c = iy * TX + ix;
-            const double v_up = iy > 0 ? cur[c - TX] : up[ix];
-            const double v_lf = ix > 0 ? cur[c - 1] : lf[iy];
-            const double v_rt = ix < TX - 1 ? cur[c + 1] : rt[iy];
-            const double v_dn = iy < TY - 1 ? cur[c + TX] : dn[ix];
-            double acc = fma(w[c][0], v_up, 0.0);
-            acc = fma(w[c][1], v_lf, acc);
-            acc = fma(w[c][2], cur[c], acc);
-            acc = fma(w[c][3], v_rt, acc);
-            acc = fma(w[c][4], v_dn, acc);
-            x[c] = p0r[c] + acc;                                        // p_initial + sum   maxent.py:110
-        }
+    stencil_tile_update<TY, TX, true>(w, p0r, cur, up, dn, lf, rt, x);
 #pragma unroll
     for (int c = 0; c < TY * TX; ++c) *reinterpret_cast<double *>(smem + own + 8 * c + OFF_W) = x[c];
 }
@@ -99,25 +84,7 @@ __global__ void __launch_bounds__(MAXT, 1) svf_grid5_cluster_kernel(const SvfBat
         for (int ix = 0; ix < TX; ++ix) {
             const int c = iy * TX + ix;
             const int s = (gty * TY + iy) * n + tx * TX + ix;
-#pragma unroll
-            for (int k = 0; k < 5; ++k) w[c][k] = 0.0;
-            if (live) {
-#pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    const int pred = a.idx[(size_t)j * S + s];
-                    double acc = 0.0;
-#pragma unroll
-                    for (int aa = 0; aa < A; ++aa)
-                        acc = fma(__ldg(a.p + ((size_t)aa * K + j) * S + s), a.policy[(size_t)pred * A + aa], acc);
-                    if (a.term[pred]) acc = 0.0;
-                    const int off = pred - s;
-                    w[c][0] += (off == -n) ? acc : 0.0;
-                    w[c][1] += (off == -1) ? acc : 0.0;
-                    w[c][2] += (off == 0) ? acc : 0.0;
-                    w[c][3] += (off == 1) ? acc : 0.0;
-                    w[c][4] += (off == n) ? acc : 0.0;
-                }
-            }
+            svf_stencil_weights<A, K>(a, S, s, n, live, w[c]);
             p0r[c] = live ? a.p0[s] : 0.0;
             cur[c] = 0.0;
             *reinterpret_cast<double *>(smem_raw + own + 8 * c) = 0.0;
@@ -289,22 +256,7 @@ __device__ __forceinline__ int svf_push_iter(unsigned char *smem, const uint32_t
         lf[iy] = *reinterpret_cast<const double *>(smem + nb_lf + 8 * (iy * TX + TX - 1) + OFF_R);
         rt[iy] = *reinterpret_cast<const double *>(smem + nb_rt + 8 * (iy * TX) + OFF_R);
     }
-#pragma unroll
-    for (int iy = 0; iy < TY; ++iy)
-#pragma unroll
-        for (int ix = 0; ix < TX; ++ix) {
-            const int c = iy * TX + ix;
-            const double v_up = iy > 0 ? cur[c - TX] : up[ix];
-            const double v_lf = ix > 0 ? cur[c - 1] : lf[iy];
-            const double v_rt = ix < TX - 1 ? cur[c + 1] : rt[iy];
-            const double v_dn = iy < TY - 1 ? cur[c + TX] : dn[ix];
-            double acc = fma(w[c][0], v_up, 0.0);
-            acc = fma(w[c][1], v_lf, acc);
-            acc = fma(w[c][2], cur[c], acc);
-            acc = fma(w[c][3], v_rt, acc);
-            acc = fma(w[c][4], v_dn, acc);
-            x[c] = p0r[c] + acc;                                        // p_initial + sum   maxent.py:110
-        }
+    stencil_tile_update<TY, TX, true>(w, p0r, cur, up, dn, lf, rt, x);
     // boundary rows first: they have the longest way to go
     if (push_up) {
 #pragma unroll
@@ -387,25 +339,7 @@ __global__ void __launch_bounds__(MAXT, 1) svf_grid5_push_kernel(const SvfBatch 
         for (int ix = 0; ix < TX; ++ix) {
             const int c = iy * TX + ix;
             const int s = (gty * TY + iy) * n + tx * TX + ix;
-#pragma unroll
-            for (int k = 0; k < 5; ++k) w[c][k] = 0.0;
-            if (live) {
-#pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    const int pred = a.idx[(size_t)j * S + s];
-                    double acc = 0.0;
-#pragma unroll
-                    for (int aa = 0; aa < A; ++aa)
-                        acc = fma(__ldg(a.p + ((size_t)aa * K + j) * S + s), a.policy[(size_t)pred * A + aa], acc);
-                    if (a.term[pred]) acc = 0.0;
-                    const int off = pred - s;
-                    w[c][0] += (off == -n) ? acc : 0.0;
-                    w[c][1] += (off == -1) ? acc : 0.0;
-                    w[c][2] += (off == 0) ? acc : 0.0;
-                    w[c][3] += (off == 1) ? acc : 0.0;
-                    w[c][4] += (off == n) ? acc : 0.0;
-                }
-            }
+            svf_stencil_weights<A, K>(a, S, s, n, live, w[c]);
             p0r[c] = live ? a.p0[s] : 0.0;
             cur[c] = 0.0;
             *reinterpret_cast<double *>(smem_raw + own + 8 * c) = 0.0;
@@ -507,22 +441,7 @@ __device__ __forceinline__ bool bwd_push_iter(unsigned char *smem, const uint32_
         lf[iy] = *reinterpret_cast<const double *>(smem + nb_lf + 8 * (iy * TX + TX - 1) + OFF_R);
         rt[iy] = *reinterpret_cast<const double *>(smem + nb_rt + 8 * (iy * TX) + OFF_R);
     }
-#pragma unroll
-    for (int iy = 0; iy < TY; ++iy)
-#pragma unroll
-        for (int ix = 0; ix < TX; ++ix) {
-            const int c = iy * TX + ix;
-            const double v_up = iy > 0 ? cur[c - TX] : up[ix];
-            const double v_lf = ix > 0 ? cur[c - 1] : lf[iy];
-            const double v_rt = ix < TX - 1 ? cur[c + 1] : rt[iy];
-            const double v_dn = iy < TY - 1 ? cur[c + TX] : dn[ix];
-            double acc = fma(w[c][0], v_up, 0.0);
-            acc = fma(w[c][1], v_lf, acc);
-            acc = fma(w[c][2], cur[c], acc);
-            acc = fma(w[c][3], v_rt, acc);
-            acc = fma(w[c][4], v_dn, acc);
-            x[c] = acc;
-        }
+    stencil_tile_update<TY, TX, false>(w, cur, cur, up, dn, lf, rt, x);
     if (rescale) {
         // exact power-of-two rescale by the exponent of the cluster-wide maximum (range extension)
         const int rp = n_rescale & 1;
@@ -628,29 +547,7 @@ __global__ void __launch_bounds__(MAXT, 1) backward_grid5_push_kernel(const Succ
         for (int ix = 0; ix < TX; ++ix) {
             const int c = iy * TX + ix;
             const int s = (gty * TY + iy) * n + tx * TX + ix;
-#pragma unroll
-            for (int k = 0; k < 5; ++k) w[c][k] = 0.0;
-            double z0 = 0.0;
-            if (live) {
-                const double r = a.reward[s];
-                max_abs_r = fmax(max_abs_r, fabs(r));
-                const double er = exp(r);                                   // np.exp(reward)   :142
-#pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    const int succ = a.idx[(size_t)j * S + s];
-                    double q = 0.0;
-#pragma unroll
-                    for (int aa = 0; aa < A; ++aa) q += __ldg(a.p + ((size_t)aa * K + j) * S + s);
-                    q *= er;
-                    const int off = succ - s;
-                    w[c][0] += (off == -n) ? q : 0.0;
-                    w[c][1] += (off == -1) ? q : 0.0;
-                    w[c][2] += (off == 0) ? q : 0.0;
-                    w[c][3] += (off == 1) ? q : 0.0;
-                    w[c][4] += (off == n) ? q : 0.0;
-                }
-                z0 = a.term[s] ? 1.0 : 0.0;                                 // zs[terminal] = 1.0  :146-147
-            }
+            const double z0 = backward_stencil_weights<A, K>(a, S, s, n, live, w[c], max_abs_r);
             cur[c] = z0;
             *reinterpret_cast<double *>(smem_raw + own + 8 * c) = z0;
             *reinterpret_cast<double *>(smem_raw + own + 8 * c + Cfg::STRIDE) = 0.0;

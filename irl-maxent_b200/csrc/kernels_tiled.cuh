@@ -20,6 +20,91 @@ namespace irlb200 {
 // (s-n, s-1, s, s+1, s+n); a neighbour that is absent from the table enters as
 // fma(0, v, acc) == acc, so results are bit-identical to svf_cta_fast_kernel.
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// Per-cell prologues shared by every stencil kernel (one CTA, cluster, push): the table row of a cell
+// folded into five weights by stencil position (s-n, s-1, s, s+1, s+n).  At most one table entry per
+// position carries weight; padding entries add +0.
+// ---------------------------------------------------------------------------
+// forward pass: W[j] = sum_a P[pred_j, s, a] * policy[pred_j, a], 0 when pred_j is terminal (maxent.py:98-110)
+template <int A, int K>
+__device__ __forceinline__ void svf_stencil_weights(const SvfArgs &a, const int S, const int s, const int n,
+                                                    const bool live, double (&w)[5]) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) w[k] = 0.0;
+    if (!live) return;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const int pred = a.idx[(size_t)j * S + s];
+        double acc = 0.0;
+#pragma unroll
+        for (int aa = 0; aa < A; ++aa)
+            acc = fma(__ldg(a.p + ((size_t)aa * K + j) * S + s), a.policy[(size_t)pred * A + aa], acc);
+        if (a.term[pred]) acc = 0.0;
+        const int off = pred - s;
+        w[0] += (off == -n) ? acc : 0.0;
+        w[1] += (off == -1) ? acc : 0.0;
+        w[2] += (off == 0) ? acc : 0.0;
+        w[3] += (off == 1) ? acc : 0.0;
+        w[4] += (off == n) ? acc : 0.0;
+    }
+}
+
+// backward pass: merged weights er * sum_a P[s, succ_j, a]; returns the start value zs0 of the cell and
+// folds |reward| into max_abs_r (maxent.py:142, :146-147, :155-156)
+template <int A, int K>
+__device__ __forceinline__ double backward_stencil_weights(const SuccArgs &a, const int S, const int s, const int n,
+                                                           const bool live, double (&w)[5], double &max_abs_r) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) w[k] = 0.0;
+    if (!live) return 0.0;
+    const double r = a.reward[s];
+    max_abs_r = fmax(max_abs_r, fabs(r));
+    const double er = exp(r);                                   // np.exp(reward)   :142
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const int succ = a.idx[(size_t)j * S + s];
+        double q = 0.0;
+#pragma unroll
+        for (int aa = 0; aa < A; ++aa) q += __ldg(a.p + ((size_t)aa * K + j) * S + s);
+        q *= er;
+        const int off = succ - s;
+        w[0] += (off == -n) ? q : 0.0;
+        w[1] += (off == -1) ? q : 0.0;
+        w[2] += (off == 0) ? q : 0.0;
+        w[3] += (off == 1) ? q : 0.0;
+        w[4] += (off == n) ? q : 0.0;
+    }
+    return a.term[s] ? 1.0 : 0.0;                               // zs[terminal] = 1.0  :146-147
+}
+
+// The arithmetic of one sweep over a thread's TY x TX tile: per cell the ascending-neighbour FMA chain
+// (s-n, s-1, s, s+1, s+n) of the ELL kernels, neighbours from the tile itself or from the halo values
+// `up` / `dn` / `lf` / `rt`; ADD_P0: `p_initial + sum` (forward pass, maxent.py:110), else the plain
+// sum (merged-weight backward sweep, maxent.py:155-156).  Stated once so that every stencil kernel is
+// bitwise identical to the others.
+template <int TY, int TX, bool ADD_P0>
+__device__ __forceinline__ void stencil_tile_update(const double (&w)[TY * TX][5], const double (&p0r)[TY * TX],
+                                                    const double (&cur)[TY * TX], const double (&up)[TX],
+                                                    const double (&dn)[TX], const double (&lf)[TY],
+                                                    const double (&rt)[TY], double (&x)[TY * TX]) {
+#pragma unroll
+    for (int iy = 0; iy < TY; ++iy)
+#pragma unroll
+        for (int ix = 0; ix < TX; ++ix) {
+            const int c = iy * TX + ix;
+            const double v_up = iy > 0 ? cur[c - TX] : up[ix];
+            const double v_lf = ix > 0 ? cur[c - 1] : lf[iy];
+            const double v_rt = ix < TX - 1 ? cur[c + 1] : rt[iy];
+            const double v_dn = iy < TY - 1 ? cur[c + TX] : dn[ix];
+            double acc = fma(w[c][0], v_up, 0.0);
+            acc = fma(w[c][1], v_lf, acc);
+            acc = fma(w[c][2], cur[c], acc);
+            acc = fma(w[c][3], v_rt, acc);
+            acc = fma(w[c][4], v_dn, acc);
+            x[c] = ADD_P0 ? p0r[c] + acc : acc;
+        }
+}
+
 template <int TY, int TX, int MAXT>
 struct Grid5Cfg {
     static constexpr int C = TY * TX;
@@ -43,22 +128,7 @@ __device__ __forceinline__ void svf_grid5_sweep(unsigned char *smem, uint32_t ow
         lf[iy] = *reinterpret_cast<const double *>(smem + nb_lf + 8 * (iy * TX + TX - 1) + OFF_R);
         rt[iy] = *reinterpret_cast<const double *>(smem + nb_rt + 8 * (iy * TX) + OFF_R);
     }
-#pragma unroll
-    for (int iy = 0; iy < TY; ++iy)
-#pragma unroll
-        for (int ix = 0; ix < TX; ++ix) {
-            const int c = iy * TX + ix;
-            const double v_up = iy > 0 ? cur[c - TX] : up[ix];
-            const double v_lf = ix > 0 ? cur[c - 1] : lf[iy];
-            const double v_rt = ix < TX - 1 ? cur[c + 1] : rt[iy];
-            const double v_dn = iy < TY - 1 ? cur[c + TX] : dn[ix];
-            double acc = fma(w[c][0], v_up, 0.0);
-            acc = fma(w[c][1], v_lf, acc);
-            acc = fma(w[c][2], cur[c], acc);
-            acc = fma(w[c][3], v_rt, acc);
-            acc = fma(w[c][4], v_dn, acc);
-            x[c] = p0r[c] + acc;                                        // p_initial + sum   maxent.py:110
-        }
+    stencil_tile_update<TY, TX, true>(w, p0r, cur, up, dn, lf, rt, x);
 #pragma unroll
     for (int c = 0; c < TY * TX; ++c) *reinterpret_cast<double *>(smem + own + 8 * c + OFF_W) = x[c];
 }
@@ -119,26 +189,7 @@ __global__ void __launch_bounds__(MAXT, MINB) svf_grid5_kernel(const SvfBatch bt
         for (int ix = 0; ix < TX; ++ix) {
             const int c = iy * TX + ix;
             const int s = (ty * TY + iy) * n + tx * TX + ix;
-#pragma unroll
-            for (int k = 0; k < 5; ++k) w[c][k] = 0.0;
-            if (live) {
-#pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    const int pred = a.idx[(size_t)j * S + s];
-                    double acc = 0.0;
-#pragma unroll
-                    for (int aa = 0; aa < A; ++aa)
-                        acc = fma(__ldg(a.p + ((size_t)aa * K + j) * S + s), a.policy[(size_t)pred * A + aa], acc);
-                    if (a.term[pred]) acc = 0.0;
-                    const int off = pred - s;
-                    // at most one table entry per offset carries weight; padding entries add +0
-                    w[c][0] += (off == -n) ? acc : 0.0;
-                    w[c][1] += (off == -1) ? acc : 0.0;
-                    w[c][2] += (off == 0) ? acc : 0.0;
-                    w[c][3] += (off == 1) ? acc : 0.0;
-                    w[c][4] += (off == n) ? acc : 0.0;
-                }
-            }
+            svf_stencil_weights<A, K>(a, S, s, n, live, w[c]);
             p0r[c] = live ? a.p0[s] : 0.0;
             cur[c] = 0.0;
             *reinterpret_cast<double *>(smem_raw + own + 8 * c) = 0.0;
@@ -213,22 +264,7 @@ __device__ __forceinline__ double lin_grid5_sweep(unsigned char *smem, uint32_t 
         rt[iy] = *reinterpret_cast<const double *>(smem + nb_rt + 8 * (iy * TX) + OFF_R);
     }
     double m = 0.0;
-#pragma unroll
-    for (int iy = 0; iy < TY; ++iy)
-#pragma unroll
-        for (int ix = 0; ix < TX; ++ix) {
-            const int c = iy * TX + ix;
-            const double v_up = iy > 0 ? cur[c - TX] : up[ix];
-            const double v_lf = ix > 0 ? cur[c - 1] : lf[iy];
-            const double v_rt = ix < TX - 1 ? cur[c + 1] : rt[iy];
-            const double v_dn = iy < TY - 1 ? cur[c + TX] : dn[ix];
-            double acc = fma(w[c][0], v_up, 0.0);
-            acc = fma(w[c][1], v_lf, acc);
-            acc = fma(w[c][2], cur[c], acc);
-            acc = fma(w[c][3], v_rt, acc);
-            acc = fma(w[c][4], v_dn, acc);
-            x[c] = acc;
-        }
+    stencil_tile_update<TY, TX, false>(w, cur, cur, up, dn, lf, rt, x);
 #pragma unroll
     for (int c = 0; c < TY * TX; ++c) {
         *reinterpret_cast<double *>(smem + own + 8 * c + OFF_W) = x[c];
@@ -268,29 +304,7 @@ __global__ void __launch_bounds__(MAXT, MINB) backward_grid5_kernel(const SuccBa
         for (int ix = 0; ix < TX; ++ix) {
             const int c = iy * TX + ix;
             const int s = (ty * TY + iy) * n + tx * TX + ix;
-#pragma unroll
-            for (int k = 0; k < 5; ++k) w[c][k] = 0.0;
-            double z0 = 0.0;
-            if (live) {
-                const double r = a.reward[s];
-                max_abs_r = fmax(max_abs_r, fabs(r));
-                const double er = exp(r);                                   // np.exp(reward)   :142
-#pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    const int succ = a.idx[(size_t)j * S + s];
-                    double q = 0.0;
-#pragma unroll
-                    for (int aa = 0; aa < A; ++aa) q += __ldg(a.p + ((size_t)aa * K + j) * S + s);
-                    q *= er;
-                    const int off = succ - s;
-                    w[c][0] += (off == -n) ? q : 0.0;
-                    w[c][1] += (off == -1) ? q : 0.0;
-                    w[c][2] += (off == 0) ? q : 0.0;
-                    w[c][3] += (off == 1) ? q : 0.0;
-                    w[c][4] += (off == n) ? q : 0.0;
-                }
-                z0 = a.term[s] ? 1.0 : 0.0;                                 // zs[terminal] = 1.0  :146-147
-            }
+            const double z0 = backward_stencil_weights<A, K>(a, S, s, n, live, w[c], max_abs_r);
             cur[c] = z0;
             *reinterpret_cast<double *>(smem_raw + own + 8 * c) = z0;
             *reinterpret_cast<double *>(smem_raw + own + 8 * c + STRIDE) = 0.0;
