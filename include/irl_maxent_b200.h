@@ -192,6 +192,17 @@ int irlb200_svf(const irlb200_tables *t, int B, const double *p_initial, int p0_
                 double *svf, const double *e_features, int ef_shared, double *grad,
                 int32_t *n_iter, int32_t *status, int mode, void *stream);
 
+/* The same call with a launch-order hint for batches: `order` [B] int32 (device) is a permutation of
+ * 0..B-1, block i of the one-CTA-per-problem launch works on problem order[i] (NULL: identity).
+ * Results are independent of the order; sorting the problems longest-first (e.g. by the sweep
+ * counts `n_iter` of the previous gradient step) removes the tail of a batch whose forward passes
+ * differ in length by several x.  Ignored by the cluster / cooperative-grid modes. */
+int irlb200_svf_ordered(const irlb200_tables *t, int B, const double *p_initial, int p0_shared,
+                        const uint8_t *terminal_mask, int mask_shared, const double *policy,
+                        double eps, int max_sweeps,
+                        double *svf, const double *e_features, int ef_shared, double *grad,
+                        int32_t *n_iter, int32_t *status, int mode, const int32_t *order, void *stream);
+
 /* ------------------------------------------------------------------------- *
  * fused gradient step: (2)+(4) or (3)+(4) in ONE launch per batch --
  * compute_expected_svf maxent.py:162-193 / compute_expected_causal_svf :344-380,
@@ -229,7 +240,7 @@ int irlb200_slab_weights(int cnt, int A, int K, const int32_t *pred_idx, const d
 /* ------------------------------------------------------------------------- *
  * slab mode with the halo exchange inside the kernel (NVLink peer stores, no collective call).
  * Every rank owns a block of irlb200_slab_block_bytes(S_total) bytes from irlb200_peer_alloc
- * ([1 KiB barrier/flag header | iterate buffer 0 [S_total] | iterate buffer 1 [S_total]]),
+ * ([4 KiB barrier/flag header | iterate buffer 0 [S_total] | iterate buffer 1 [S_total]]),
  * exports it with irlb200_ipc_export (64-byte CUDA IPC handle, exchanged by the host layer over
  * torch.distributed) and maps the others with irlb200_ipc_import.  The header must be zero on all
  * ranks before any rank launches.  irlb200_slab_persistent runs one whole fixed point of the
@@ -259,6 +270,21 @@ int    irlb200_slab_persistent(int op, int rank, int world, void *const *blocks,
                                double eps, int max_sweeps, int vi_mean, double *out, double *policy_out,
                                int32_t *n_iter, int32_t *status, double timeout_s, int overlap,
                                void *stream);
+
+/* Slab mode without a per-sweep barrier (csrc/slab_flow.cu): same arguments, blocks, header and
+ * results as irlb200_slab_persistent, but every persistent CTA owns a fixed range of states and waits
+ * only for the CTAs (and, on the slab's first / last grid row, the neighbouring GPU) within one grid
+ * row of it; the stop rule is all-reduced once per `chunk` sweeps (<= 64; <= 0: default 32) and the
+ * exact stopping sweep of the reference (maxent.py:108,326; solver.py:40) is reproduced by
+ * snapshot-and-replay inside the kernel.  `work` is a caller-owned device buffer of at least
+ * irlb200_slab_flow_work_bytes(cnt) bytes, private to this call (not peer-mapped; any contents). */
+size_t irlb200_slab_flow_work_bytes(int cnt);
+int    irlb200_slab_flow(int op, int rank, int world, void *const *blocks, int S_total, int lo, int cnt,
+                         int halo, int A, int K, const int32_t *idx, const double *p, const double *c0,
+                         const double *c1, const double *policy_in, const uint8_t *terminal_mask,
+                         double *w_scratch, double discount, double eps, int max_sweeps, int vi_mean,
+                         double *out, double *policy_out, int32_t *n_iter, int32_t *status,
+                         double timeout_s, int chunk, void *work, size_t work_bytes, void *stream);
 
 /* ------------------------------------------------------------------------- *
  * dense feature products on the path: reward = features . theta (maxent.py:244)

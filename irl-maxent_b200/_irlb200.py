@@ -67,10 +67,15 @@ SIGNATURES = {
     "irlb200_slab_reset": ([_vp, _vp], _i),
     "irlb200_slab_persistent": ([_i, _i, _i, ctypes.POINTER(ctypes.c_void_p), _i, _i, _i, _i, _i, _i, _vp, _vp, _vp,
                                  _vp, _vp, _vp, _vp, _d, _d, _i, _i, _vp, _vp, _vp, _vp, _d, _i, _vp], _i),
+    "irlb200_slab_flow_work_bytes": ([_i], ctypes.c_size_t),
+    "irlb200_slab_flow": ([_i, _i, _i, ctypes.POINTER(ctypes.c_void_p), _i, _i, _i, _i, _i, _i, _vp, _vp, _vp,
+                           _vp, _vp, _vp, _vp, _d, _d, _i, _i, _vp, _vp, _vp, _vp, _d, _i, _vp, ctypes.c_size_t,
+                           _vp], _i),
     "irlb200_backward": ([_tp, _i, _vp, _vp, _i, _i, _vp, _i, _vp], _i),
     "irlb200_soft_vi": ([_tp, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _i, _vp], _i),
     "irlb200_value_iteration": ([_tp, _i, _vp, _d, _d, _i, _i, _vp, _vp, _vp, _i, _vp], _i),
     "irlb200_svf": ([_tp, _i, _vp, _i, _vp, _i, _vp, _d, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp], _i),
+    "irlb200_svf_ordered": ([_tp, _i, _vp, _i, _vp, _i, _vp, _d, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp], _i),
     "irlb200_expected_svf": ([_tp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _d, _d, _d, _i,
                               _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "irlb200_sample_trajectories": ([_tp, _vp, _vp, _vp, _i, _i, ctypes.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
@@ -457,10 +462,24 @@ def value_iteration(tables, reward, discount, eps=1e-3, max_sweeps=None, mean=Fa
     return val
 
 
+# Batches whose forward passes differ in length by several x (IcyGridWorld batch of the bench: mean 45 k,
+# max 174 k sweeps) leave SMs idle behind the last long worlds when launched in index order.  The sweep
+# counts of one gradient step predict the next one's (omega moves little per step), so every batched
+# forward launch stores "longest first" as the launch order of the next launch on the same tables.
+# Scheduling only: results do not depend on the order.  IRLB200_LPT=0 disables it.
+LPT_MIN_BATCH = 256
+
+
+def _lpt_enabled():
+    return os.environ.get("IRLB200_LPT", "1") != "0"
+
+
 def svf(tables, p_initial, terminal_mask_t, policy, eps=1e-5, max_sweeps=None, e_features=None,
-        mode=MODE_AUTO):
+        mode=MODE_AUTO, order="auto"):
     """(4) expected_svf_from_policy, maxent.py:63-114.  policy [S,A] or [B,S,A].
-    With e_features ([S] or [B,S], identity features) also returns grad = e_features - svf."""
+    With e_features ([S] or [B,S], identity features) also returns grad = e_features - svf.
+    `order`: launch-order hint for batches (int32 permutation [B] on the device), None = index order,
+    "auto" = longest-first by the sweep counts of the previous batched call on these tables."""
     global last_info
     torch = require_cuda()
     S, A = tables.S, tables.A
@@ -481,10 +500,21 @@ def svf(tables, p_initial, terminal_mask_t, policy, eps=1e-5, max_sweeps=None, e
     status = torch.empty(B, dtype=torch.int32, device=pol.device)
     ct = tables.c_struct(_tables_shared(tables, B))
     ms = DEFAULT_MAX_SWEEPS if max_sweeps is None else int(max_sweeps)
+    auto = isinstance(order, str)
+    if auto:
+        hint = getattr(tables, "_svf_order", None)
+        order = hint if (hint is not None and hint.numel() == B and hint.device == pol.device and _lpt_enabled()) else None
+    elif order is not None:
+        order = to_device(order, torch.int32)
+        if order.numel() != B:
+            raise EngineError("order must be a permutation of the %d problems" % B)
     with _timed("svf"):
-        _check(_lib.irlb200_svf(ctypes.byref(ct), B, _ptr(p0), p0shared, _ptr(mask), mshared, _ptr(pol), float(eps), ms,
-                                _ptr(out), _ptr(ef), efshared, _ptr(grad), _ptr(n_iter), _ptr(status), mode,
-                                _stream()))
+        _check(_lib.irlb200_svf_ordered(ctypes.byref(ct), B, _ptr(p0), p0shared, _ptr(mask), mshared, _ptr(pol),
+                                        float(eps), ms, _ptr(out), _ptr(ef), efshared, _ptr(grad), _ptr(n_iter),
+                                        _ptr(status), mode, _ptr(order), _stream()))
+    if auto and B >= LPT_MIN_BATCH and _lpt_enabled():
+        # device-side argsort, no host sync; used by the next call on the same tables
+        tables._svf_order = torch.argsort(n_iter, descending=True, stable=True).to(torch.int32)
     last_info = SweepInfo(n_iter, status)
     return (out, grad) if grad is not None else out
 

@@ -22,7 +22,14 @@ struct SvfBatch {
     size_t p0_stride, term_stride, ef_stride;
     int32_t *n_iter, *status;
     int out_stride;
+    const int32_t *order;        // [B] or null: block i works on problem order[i] (a permutation; launch-order
+                                 // hint, e.g. longest-first from the previous gradient step's sweep counts)
 };
+
+// problem handled by this block of a one-CTA-per-problem forward launch
+__device__ __forceinline__ size_t svf_problem(const SvfBatch &bt) {
+    return bt.order ? (size_t)__ldg(bt.order + blockIdx.x) : (size_t)blockIdx.x;
+}
 
 struct StepBatch {
     SuccArgs s;

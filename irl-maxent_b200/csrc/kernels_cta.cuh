@@ -23,9 +23,10 @@ __global__ void __launch_bounds__(MAXT, MINB) svf_cta_kernel(const SvfBatch bt) 
     CtaTopo tp;
     SvfArgs a = bt.a;
     carve_cta(tp, a.S);
-    offset_svf(a, bt, blockIdx.x);
-    int *ni = bt.n_iter ? bt.n_iter + (size_t)blockIdx.x * bt.out_stride : nullptr;
-    int *st = bt.status ? bt.status + (size_t)blockIdx.x * bt.out_stride : nullptr;
+    const size_t b = svf_problem(bt);
+    offset_svf(a, bt, b);
+    int *ni = bt.n_iter ? bt.n_iter + b * bt.out_stride : nullptr;
+    int *st = bt.status ? bt.status + b * bt.out_stride : nullptr;
     svf_phase<CtaTopo, A_T, K_T, SPT_T>(tp, a, ni, st);
 }
 
@@ -256,7 +257,8 @@ __global__ void __launch_bounds__(MAXT, MINB) svf_cta_fast_kernel(const SvfBatch
     int *flag = reinterpret_cast<int *>(smem_raw + 2 * STRIDE);
 
     SvfArgs a = bt.a;
-    offset_svf(a, bt, blockIdx.x);
+    const size_t prob = svf_problem(bt);
+    offset_svf(a, bt, prob);
     const int S = a.S, T = blockDim.x, tid = threadIdx.x;
 
     double w[SPT][K], p0r[SPT], cur[SPT];
@@ -316,8 +318,8 @@ __global__ void __launch_bounds__(MAXT, MINB) svf_cta_fast_kernel(const SvfBatch
         }
     }
     if (tid == 0) {
-        if (bt.n_iter) bt.n_iter[(size_t)blockIdx.x * bt.out_stride] = n;
-        if (bt.status) bt.status[(size_t)blockIdx.x * bt.out_stride] = status;
+        if (bt.n_iter) bt.n_iter[prob * bt.out_stride] = n;
+        if (bt.status) bt.status[prob * bt.out_stride] = status;
     }
 }
 

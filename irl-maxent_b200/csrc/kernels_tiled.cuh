@@ -169,7 +169,8 @@ __global__ void __launch_bounds__(MAXT, MINB) svf_grid5_kernel(const SvfBatch bt
     int *flag = reinterpret_cast<int *>(smem_raw + 2 * STRIDE);
 
     SvfArgs a = bt.a;
-    offset_svf(a, bt, blockIdx.x);
+    const size_t prob = svf_problem(bt);
+    offset_svf(a, bt, prob);
     const int S = a.S, tid = threadIdx.x;
     const int ntx = n / TX, nty = n / TY;
     const bool live = tid < ntx * nty;
@@ -231,8 +232,8 @@ __global__ void __launch_bounds__(MAXT, MINB) svf_grid5_kernel(const SvfBatch bt
             }
     }
     if (tid == 0) {
-        if (bt.n_iter) bt.n_iter[(size_t)blockIdx.x * bt.out_stride] = nsw;
-        if (bt.status) bt.status[(size_t)blockIdx.x * bt.out_stride] = status;
+        if (bt.n_iter) bt.n_iter[prob * bt.out_stride] = nsw;
+        if (bt.status) bt.status[prob * bt.out_stride] = status;
     }
 }
 

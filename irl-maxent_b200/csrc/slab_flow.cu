@@ -1,0 +1,403 @@
+// slab_flow.cu -- slab mode without a per-sweep barrier ("dataflow" sweeps).
+//
+// slab_persistent.cu fences every sweep with a full barrier: all CTAs of the GPU arrive on one
+// counter, the last one exchanges (sequence, votes) with EVERY rank and releases the others
+// (2.7 us locally + an all-to-all NVLink flag round per sweep, against 6 us of HBM time per sweep
+// of a 2048 x 2048 world on 8 GPUs).  A grid world's sweep only couples a state to the states one
+// grid row away, so nothing in the arithmetic needs that:
+//
+//   * every persistent CTA owns a FIXED contiguous range of the slab's states and publishes, after
+//     each sweep, one progress word (release store).  Before sweep k it waits only for the few CTAs
+//     whose ranges lie within one grid row of its own to have finished sweep k-1 -- which is both
+//     the read-after-write condition (their rows are my halo) and the write-after-read condition
+//     (they have finished reading the buffer I am about to overwrite).  CTAs of one SM drift apart
+//     by a fraction of a sweep, so one CTA's wait is hidden behind another's loads;
+//   * across GPUs the same rule holds between the CTAs that own the first / last grid row of
+//     neighbouring slabs: they push their row into the neighbour's ghost row with NVLink peer
+//     stores, fence at system scope, count themselves on a local counter, and the last one raises
+//     ONE data flag in the neighbour's header.  No all-to-all, no collective call;
+//   * the stop rule (`while delta > eps`, maxent.py:108,326; solver.py:40) needs the maximum over
+//     ALL states, but not immediately: every CTA records one vote bit per sweep, and only every
+//     `chunk` sweeps the masks are OR-ed over the GPU and exchanged between the ranks behind one
+//     full barrier.  To return exactly the iterate and the sweep count of the reference, the
+//     iterate at the start of each chunk is snapshotted on the fly (one extra 8-byte store per state
+//     in the first sweep of a chunk); when the masks show that the loop ended at sweep i of the
+//     chunk, the snapshot is restored and sweeps 0..i are replayed (deterministic arithmetic:
+//     bitwise the same values).  Cost: < 2 chunks of extra sweeps per fixed point.
+//
+// Spin loops carry a wall-clock timeout and watch an abort word, so a missing peer ends the launch
+// with IRLB200_ST_ABORTED instead of hanging the GPU.  Same per-state arithmetic (slab_common.cuh)
+// and therefore bitwise the same results as every other kernel of the library.
+#include <cstdlib>
+
+#include "host_util.h"
+#include "slab_common.cuh"
+
+namespace irlb200 {
+
+struct FlowShared {                               // at byte kFlowOffset of every rank's peer-mapped header
+    unsigned long long gflag[2];                  // [0]: rank-1's last row, [1]: rank+1's first row complete through v-1 sweeps
+    unsigned long long bcount[2];                 // local: low / high boundary CTAs that published, monotonic
+    unsigned long long abort;                     // != 0: somebody timed out
+    unsigned long long pad[3];
+    unsigned long long vgt[2], vnan[2];           // vote masks of the current chunk (bit i = sweep i), by barrier parity
+    unsigned long long rel_gt[4], rel_nan[4];     // decision masks broadcast with the barrier release
+    unsigned long long xgt[2][kMaxRanks], xnan[2][kMaxRanks];   // masks received from the other ranks
+};
+constexpr size_t kFlowOffset = 1024;
+static_assert(sizeof(SlabShared) <= kFlowOffset, "SlabShared grew into the flow header");
+static_assert(kFlowOffset + sizeof(FlowShared) <= kSlabHeaderBytes, "flow header does not fit");
+constexpr int kProgressStride = 4;                // progress words 32 bytes apart (one sector each)
+
+__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v) {
+    *(volatile unsigned long long *)p = v;
+}
+
+template <int OP, int A_T, int K_T>
+__global__ void __launch_bounds__(256, OP == 3 ? 4 : 3)
+    slab_flow_kernel(const OverlapArgs a, const SlabPeers pe, unsigned char *base, unsigned long long *progress,
+                     double *snap, const int chunk, const int edge, int32_t *n_iter, int32_t *status) {
+    __shared__ unsigned long long s_gt, s_nanmask;
+    __shared__ int s_nan, s_dead;
+    constexpr int QN = A_T > 0 ? A_T : kMaxDynA;
+    SlabShared *sh = reinterpret_cast<SlabShared *>(base);
+    FlowShared *fs = reinterpret_cast<FlowShared *>(base + kFlowOffset);
+    double *buf0 = reinterpret_cast<double *>(base + kSlabHeaderBytes), *buf1 = buf0 + a.S_total;
+    const int tid = threadIdx.x, cta = blockIdx.x, nthr = blockDim.x, nb = gridDim.x;
+    const int G = pe.world, me = pe.rank, lo = a.lo, cnt = a.cnt, h = a.halo;
+    const bool has_lo = pe.lo_buf0 != nullptr, has_hi = pe.hi_buf0 != nullptr;
+    const int A = A_T > 0 ? A_T : a.A, K = K_T > 0 ? K_T : a.K;
+
+    // ---- fixed ownership and the dependence set ----------------------------------------------
+    // Three zones of contiguous, near-equal ranges: the slab's first grid row (when rank-1 exists) is split
+    // over `edge` CTAs, its last row (when rank+1 exists) over another `edge`, the interior over the rest.
+    // About one state per thread on the edge rows: their CTAs finish a sweep in a fraction of the time the
+    // interior CTAs need, so the NVLink flight of the boundary row (system fence + flag, ~3 us) runs
+    // while the interior is still being swept instead of adding to every sweep.  edge == 0: uniform split.
+    const int eL = has_lo ? edge : 0, eH = has_hi ? edge : 0, mid = nb - eL - eH;
+    const int z0 = eL ? h : 0, z1 = eH ? cnt - h : cnt;
+    auto ceil_div = [](long long x, long long y) { return (int)((x + y - 1) / y); };
+    auto beg_of = [&](int c) -> int {
+        if (c < eL) return (int)((long long)z0 * c / eL);
+        if (c >= nb - eH) return z1 + (int)((long long)(cnt - z1) * (c - (nb - eH)) / (eH ? eH : 1));
+        return z0 + (int)((long long)(z1 - z0) * (c - eL) / mid);
+    };
+    auto cta_of = [&](int i) -> int {                         // owner of local state i
+        if (i < z0) return ceil_div(((long long)i + 1) * eL, z0) - 1;
+        if (i >= z1) return nb - eH + ceil_div(((long long)(i - z1) + 1) * eH, cnt - z1) - 1;
+        return eL + ceil_div(((long long)(i - z0) + 1) * mid, z1 - z0) - 1;
+    };
+    const int beg = beg_of(cta), end = beg_of(cta + 1);
+    const int d_lo = cta_of(max(beg - h, 0)), d_hi = cta_of(min(end + h, cnt) - 1);
+    const bool low_push = has_lo && beg < h;                  // owns part of the first grid row: pushes to rank-1, reads its ghosts
+    const bool high_push = has_hi && end > cnt - h;
+    const unsigned long long m_lo = (unsigned long long)cta_of(min(h, cnt) - 1) + 1ull;        // CTAs with beg < h
+    const unsigned long long m_hi = (unsigned long long)(nb - cta_of(max(cnt - h, 0)));        // CTAs with end > cnt - h
+    FlowShared *fs_lo = has_lo ? reinterpret_cast<FlowShared *>(reinterpret_cast<unsigned char *>(pe.shared[me - 1]) + kFlowOffset) : nullptr;
+    FlowShared *fs_hi = has_hi ? reinterpret_cast<FlowShared *>(reinterpret_cast<unsigned char *>(pe.shared[me + 1]) + kFlowOffset) : nullptr;
+
+    unsigned seq = 0;                  // full-barrier sequence number
+    bool dead = false;
+
+    auto raise_abort = [&]() {
+        st_volatile_u64(&fs->abort, 1ull);
+        for (int r = 0; r < G; ++r)
+            if (r != me)
+                st_volatile_u64(&reinterpret_cast<FlowShared *>(reinterpret_cast<unsigned char *>(pe.shared[r]) + kFlowOffset)->abort, 1ull);
+    };
+    // wait until *p >= want (monotonic words); false = aborted / timed out
+    auto spin_ge = [&](const unsigned long long *p, unsigned long long want, bool sys) -> bool {
+        unsigned long long t0 = 0ull;
+        for (unsigned spins = 0;; ++spins) {
+            const unsigned long long v = sys ? ld_acquire_sys(p) : ld_acquire_gpu(p);
+            if (v >= want) return true;
+            if ((spins & 1023u) == 1023u) {
+                if (*(volatile unsigned long long *)&fs->abort) return false;
+                const unsigned long long now = globaltimer_ns();
+                if (!t0) t0 = now;
+                else if ((long long)(now - t0) > pe.timeout_ns) { raise_abort(); return false; }
+            }
+        }
+    };
+    // value of an owned state: local store, plus the neighbour's ghost row for boundary states
+    auto put = [&](int b, int i, double v) {
+        const int g = lo + i;
+        st_cg((b ? buf1 : buf0) + g, v);
+        if (has_lo && i < h) st_cg((b ? pe.lo_buf1 : pe.lo_buf0) + g, v);
+        if (has_hi && i >= cnt - h) st_cg((b ? pe.hi_buf1 : pe.hi_buf0) + g, v);
+    };
+    // thread 0, after a bar.sync that covers the CTA's stores: "my rows hold iterate number v - 1"
+    auto publish = [&](unsigned long long v) {
+        if (low_push || high_push) __threadfence_system(); else __threadfence();
+        st_volatile_u64(progress + (size_t)cta * kProgressStride, v);
+        if (low_push && atomicAdd(&fs->bcount[0], 1ull) + 1ull == v * m_lo) st_volatile_u64(&fs_lo->gflag[1], v);
+        if (high_push && atomicAdd(&fs->bcount[1], 1ull) + 1ull == v * m_hi) st_volatile_u64(&fs_hi->gflag[0], v);
+    };
+
+    // Full barrier over all CTAs of all ranks (once per chunk, not per sweep): local arrival counter, the
+    // last arriver ORs the chunk's vote masks, exchanges them with every rank and releases the others.
+    // Returns false when the launch is aborted.
+    auto full_barrier = [&](unsigned long long my_gt, unsigned long long my_nan, unsigned long long &all_gt,
+                            unsigned long long &all_nan) -> bool {
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned s4 = seq & 3u, par = seq & 1u;
+            const unsigned long long want = (unsigned long long)(seq + 1u);
+            if (my_gt) atomicOr(&fs->vgt[par], my_gt);
+            if (my_nan) atomicOr(&fs->vnan[par], my_nan);
+            if (low_push || high_push) __threadfence_system(); else __threadfence();   // restored rows reach the peers too
+            const unsigned long long old = atomicAdd(&sh->slot[s4], 1ull);
+            if (old == (unsigned long long)nb - 1ull) {
+                __threadfence();
+                unsigned long long mg = *(volatile unsigned long long *)&fs->vgt[par];
+                unsigned long long mn = *(volatile unsigned long long *)&fs->vnan[par];
+                fs->vgt[par] = 0ull;                         // next use: two barriers from now
+                fs->vnan[par] = 0ull;
+                bool ok = !dead;
+                if (G > 1 && ok) {
+                    for (int r = 0; r < G; ++r) {
+                        if (r == me) continue;
+                        FlowShared *fr = reinterpret_cast<FlowShared *>(reinterpret_cast<unsigned char *>(pe.shared[r]) + kFlowOffset);
+                        st_volatile_u64(&fr->xgt[par][me], mg);
+                        st_volatile_u64(&fr->xnan[par][me], mn);
+                    }
+                    __threadfence_system();                  // masks (and restored rows) before the flags
+                    for (int r = 0; r < G; ++r)
+                        if (r != me) st_volatile_u64(&pe.shared[r]->flags[par][me], want);
+                    for (int r = 0; r < G && ok; ++r) {
+                        if (r == me) continue;
+                        ok = spin_ge(&sh->flags[par][r], want, true);
+                        if (ok) {
+                            mg |= *(volatile unsigned long long *)&fs->xgt[par][r];
+                            mn |= *(volatile unsigned long long *)&fs->xnan[par][r];
+                        }
+                    }
+                }
+                sh->slot[(seq + 2u) & 3u] = 0ull;
+                fs->rel_gt[s4] = mg;
+                fs->rel_nan[s4] = mn;
+                st_release_gpu(&sh->release[s4], (want << 8) | (ok ? 0ull : 4ull));
+            }
+            unsigned long long rel, t0 = 0ull;
+            for (unsigned spins = 0;; ++spins) {
+                rel = ld_acquire_gpu(&sh->release[s4]);
+                if ((rel >> 8) == want) break;
+                if ((spins & 1023u) == 1023u) {                 // the last arriver itself gives up after timeout_ns
+                    const unsigned long long now = globaltimer_ns();
+                    if (!t0) t0 = now;
+                    else if ((long long)(now - t0) > 3 * pe.timeout_ns) { rel = 4ull; break; }
+                }
+            }
+            s_gt = *(volatile unsigned long long *)&fs->rel_gt[s4];
+            s_nanmask = *(volatile unsigned long long *)&fs->rel_nan[s4];
+            s_dead = (rel & 4ull) ? 1 : 0;
+        }
+        __syncthreads();
+        all_gt = s_gt;
+        all_nan = s_nanmask;
+        ++seq;
+        if (s_dead) dead = true;
+        return !dead;
+    };
+
+    // ---- prologue: weights (forward pass), initial iterate -------------------------------------
+    if (tid == 0) { s_nan = 0; s_dead = 0; }
+    for (int i = beg + tid; i < end; i += nthr) {
+        if (OP == 3) {
+            for (int j = 0; j < K; ++j) {
+                const int pred = a.idx[(size_t)j * cnt + i];
+                double acc = 0.0;
+                for (int aa = 0; aa < A; ++aa)
+                    acc = fma(__ldg(a.p + ((size_t)aa * K + j) * cnt + i), a.policy_in[(size_t)pred * A + aa], acc);
+                a.w[(size_t)j * cnt + i] = a.term[pred] ? 0.0 : acc;
+            }
+        }
+        put(0, i, OP == kOpSoftVI ? kNegHuge : 0.0);
+    }
+    __syncthreads();
+    if (tid == 0) publish(1ull);
+
+    // one sweep: iterate number q (buffer q & 1) -> q + 1.  Votes of the CTA go to (any_gt, any_nan) on thread 0.
+    auto sweep = [&](const unsigned q, const bool take_snap, bool &any_gt, bool &any_nan) -> bool {
+        bool ok = true;
+        const unsigned long long need = (unsigned long long)q + 1ull;
+        for (int d = d_lo + tid; d <= d_hi; d += nthr)
+            if (d != cta) ok = spin_ge(progress + (size_t)d * kProgressStride, need, false) && ok;
+        if (low_push && tid == nthr - 1) ok = spin_ge(&fs->gflag[0], need, true) && ok;
+        if (high_push && tid == nthr - 2) ok = spin_ge(&fs->gflag[1], need, true) && ok;
+        if (__syncthreads_or(ok ? 0 : 1)) return false;
+        const double *x_in = (q & 1u) ? buf1 : buf0;
+        const int bo = (int)((q + 1u) & 1u);
+        bool gt = false, nan = false;
+        for (int i = beg + tid; i < end; i += nthr) {
+            const double x = overlap_update<OP, A_T, K_T>(a, x_in, i, nullptr);
+            const double xo = ld_cg(x_in + lo + i);
+            const double diff = fabs(x - xo);
+            gt |= diff > a.eps;
+            nan |= diff != diff;
+            if (take_snap) snap[i] = xo;
+            put(bo, i, x);
+        }
+        if (nan) s_nan = 1;
+        const int any = __syncthreads_or(gt ? 1 : 0);
+        if (tid == 0) {
+            publish((unsigned long long)q + 2ull);
+            any_gt = any != 0;
+            any_nan = s_nan != 0;
+            s_nan = 0;
+        }
+        return true;
+    };
+
+    // ---- chunks of sweeps ------------------------------------------------------------------------
+    const int limit = a.max_sweeps > 0 ? a.max_sweeps : 0x7fffffff;
+    int n = 0, st = IRLB200_ST_CONVERGED;
+    unsigned q = 0;
+    for (;;) {
+        const int k = min(chunk, limit - n);
+        unsigned long long my_gt = 0ull, my_nan = 0ull;
+        bool ok = true;
+        for (int i = 0; i < k && ok; ++i) {
+            bool g = false, nn = false;
+            ok = sweep(q, i == 0, g, nn);
+            if (ok) {
+                ++q;
+                if (g) my_gt |= 1ull << i;
+                if (nn) my_nan |= 1ull << i;
+            }
+        }
+        if (!ok) dead = true;
+        unsigned long long all_gt = 0ull, all_nan = 0ull;
+        if (!full_barrier(my_gt, my_nan, all_gt, all_nan)) { st = IRLB200_ST_ABORTED; break; }
+        // first sweep of the chunk that ends the reference's loop: delta <= eps, or NaN
+        const unsigned long long kmask = k >= 64 ? ~0ull : ((1ull << k) - 1ull);
+        const unsigned long long ends = (~all_gt | all_nan) & kmask;
+        if (!ends) {
+            n += k;
+            if (n >= limit) { st = IRLB200_ST_MAXSWEEPS; break; }
+            continue;
+        }
+        const int stop = __ffsll((long long)ends) - 1;
+        st = ((all_nan >> stop) & 1ull) ? IRLB200_ST_NONFINITE : IRLB200_ST_CONVERGED;
+        if (stop == k - 1) { n += k; break; }                 // ended on the chunk's last sweep: nothing to undo
+        // restore the iterate the chunk started from and replay sweeps 0..stop
+        for (int i = beg + tid; i < end; i += nthr) put((int)(q & 1u), i, snap[i]);
+        if (!full_barrier(0ull, 0ull, all_gt, all_nan)) { st = IRLB200_ST_ABORTED; break; }
+        for (int i = 0; i <= stop && ok; ++i) {
+            bool g, nn;
+            ok = sweep(q, false, g, nn);
+            if (ok) ++q;
+        }
+        if (!ok) { st = IRLB200_ST_ABORTED; break; }
+        n += stop + 1;
+        break;
+    }
+
+    // ---- outputs ---------------------------------------------------------------------------------
+    if (st != IRLB200_ST_ABORTED) {
+        const double *x_new = (q & 1u) ? buf1 : buf0, *x_old = ((q - 1u) & 1u) ? buf1 : buf0;
+        for (int i = beg + tid; i < end; i += nthr) {
+            a.out[i] = ld_cg(x_new + lo + i);
+            if (OP == kOpSoftVI && a.policy_out && q > 0) {
+                double qv[QN];
+                const double x = overlap_update<OP, A_T, K_T>(a, x_old, i, qv);
+                for (int aa = 0; aa < A; ++aa) a.policy_out[(size_t)i * A + aa] = exp(qv[aa] - x);     // maxent.py:341
+            }
+        }
+    }
+    if (cta == 0 && tid == 0) {
+        if (n_iter) *n_iter = n;
+        if (status) *status = st;
+    }
+}
+
+}  // namespace irlb200
+
+using namespace irlb200;
+
+static int flow_env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+// bytes of the local (not peer-mapped) work buffer of irlb200_slab_flow: progress words + chunk snapshot
+extern "C" size_t irlb200_slab_flow_work_bytes(int cnt) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t prog = (size_t)sms * 8 * kProgressStride * sizeof(unsigned long long);
+    return prog + sizeof(double) * (size_t)(cnt > 0 ? cnt : 0) + 256;
+}
+
+extern "C" int irlb200_slab_flow(int op, int rank, int world, void *const *blocks, int S_total, int lo, int cnt,
+                                 int halo, int A, int K, const int32_t *idx, const double *p, const double *c0,
+                                 const double *c1, const double *policy_in, const uint8_t *terminal_mask,
+                                 double *w_scratch, double discount, double eps, int max_sweeps, int vi_mean,
+                                 double *out, double *policy_out, int32_t *n_iter, int32_t *status, double timeout_s,
+                                 int chunk, void *work, size_t work_bytes, void *stream) {
+    if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world || !blocks || cnt <= 0 || halo <= 0 || !idx || !p ||
+        !c0 || !out || !work)
+        return fail(IRLB200_EINVAL, "slab_flow: bad argument");
+    if (op < 1 || op > 3) return fail(IRLB200_EINVAL, "slab_flow: unknown op");
+    if (device_count_impl() <= 0) return fail(IRLB200_ECUDA, "no CUDA device");
+    if (!(A == 4 && (K == 5 || K == 4)) && A > kMaxDynA) return fail(IRLB200_EINVAL, "run-time A > 16 is not supported");
+    if (op == 3 && (!policy_in || !terminal_mask || !w_scratch)) return fail(IRLB200_EINVAL, "slab_flow: forward pass inputs");
+    if (op == 1 && (!c1 || !policy_out)) return fail(IRLB200_EINVAL, "slab_flow: soft-VI inputs");
+    if (world > 1 && cnt < halo) return fail(IRLB200_ELIMIT, "slab_flow: a slab must hold at least one grid row");
+    if (work_bytes < irlb200_slab_flow_work_bytes(cnt)) return fail(IRLB200_EINVAL, "slab_flow: work buffer too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    SlabPeers pe{};
+    for (int r = 0; r < world; ++r) pe.shared[r] = reinterpret_cast<SlabShared *>(blocks[r]);
+    auto bufs = [&](int r, int which) {
+        return reinterpret_cast<double *>(static_cast<unsigned char *>(blocks[r]) + kSlabHeaderBytes) + (size_t)which * S_total;
+    };
+    if (rank > 0) { pe.lo_buf0 = bufs(rank - 1, 0); pe.lo_buf1 = bufs(rank - 1, 1); }
+    if (rank < world - 1) { pe.hi_buf0 = bufs(rank + 1, 0); pe.hi_buf1 = bufs(rank + 1, 1); }
+    pe.rank = rank; pe.world = world; pe.lo = lo; pe.hi = lo + cnt; pe.halo = halo;
+    pe.timeout_ns = (long long)((timeout_s > 0 ? timeout_s : 20.0) * 1e9);
+    unsigned char *base = static_cast<unsigned char *>(blocks[rank]);
+
+    OverlapArgs oa{};
+    oa.op = op; oa.lo = lo; oa.cnt = cnt; oa.S_total = S_total; oa.halo = halo; oa.A = A; oa.K = K;
+    oa.idx = idx; oa.p = p; oa.c0 = c0; oa.c1 = c1; oa.policy_in = policy_in; oa.term = terminal_mask;
+    oa.w = w_scratch; oa.discount = discount; oa.eps = eps; oa.max_sweeps = max_sweeps; oa.vi_mean = vi_mean;
+    oa.out = out; oa.policy_out = policy_out;
+
+    const bool fast = (A == 4 && K == 5), compact = (A == 4 && K == 4);
+    const void *k = nullptr;
+    if (op == 3) k = fast ? (const void *)slab_flow_kernel<3, 4, 5> : compact ? (const void *)slab_flow_kernel<3, 4, 4> : (const void *)slab_flow_kernel<3, 0, 0>;
+    else if (op == 1) k = fast ? (const void *)slab_flow_kernel<kOpSoftVI, 4, 5> : compact ? (const void *)slab_flow_kernel<kOpSoftVI, 4, 4> : (const void *)slab_flow_kernel<kOpSoftVI, 0, 0>;
+    else k = fast ? (const void *)slab_flow_kernel<kOpVI, 4, 5> : compact ? (const void *)slab_flow_kernel<kOpVI, 4, 4> : (const void *)slab_flow_kernel<kOpVI, 0, 0>;
+
+    const int threads = 256;
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, 0);
+    if (e != cudaSuccess) return fail_cuda(e, "occupancy(slab flow)");
+    if (per_sm < 1) return fail(IRLB200_ELIMIT, "slab flow kernel does not fit on an SM");
+    if (per_sm > 8) per_sm = 8;
+    const int per_sm_env = flow_env_int("IRLB200_FLOW_CTAS_PER_SM", 0);
+    if (per_sm_env > 0 && per_sm_env < per_sm) per_sm = per_sm_env;
+    long long want = ((long long)cnt + threads - 1) / threads, cap = (long long)sms * per_sm;
+    int nb = (int)(want < cap ? want : cap);
+    const int nb_env = flow_env_int("IRLB200_FLOW_BLOCKS", 0);
+    if (nb_env > 0 && nb_env < nb) nb = nb_env;
+    if (nb < 1) nb = 1;
+    if (chunk <= 0) chunk = flow_env_int("IRLB200_FLOW_CHUNK", 32);
+    if (chunk > 64) chunk = 64;
+    // CTAs per boundary row (see the kernel): about one state per thread, at most 8
+    int edge = halo / threads;
+    edge = edge < 1 ? 1 : (edge > 8 ? 8 : edge);
+    edge = flow_env_int("IRLB200_FLOW_EDGE_CTAS", edge);
+    if (world == 1 || edge < 0 || cnt < 4 * halo || nb < 8 * edge || halo < edge) edge = 0;
+
+    unsigned long long *progress = static_cast<unsigned long long *>(work);
+    const size_t prog_bytes = (size_t)sms * 8 * kProgressStride * sizeof(unsigned long long);
+    double *snap = reinterpret_cast<double *>(static_cast<unsigned char *>(work) + ((prog_bytes + 255) & ~(size_t)255));
+    e = cudaMemsetAsync(progress, 0, prog_bytes, st);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync(slab flow progress)");
+    void *params[9] = {&oa, &pe, &base, &progress, &snap, &chunk, &edge, &n_iter, &status};
+    e = cudaLaunchCooperativeKernel(k, dim3(nb), dim3(threads), params, 0, st);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaLaunchCooperativeKernel(slab flow)");
+    return IRLB200_OK;
+}

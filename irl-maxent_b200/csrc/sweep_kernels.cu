@@ -660,6 +660,15 @@ extern "C" int irlb200_svf(const irlb200_tables *t, int B, const double *p_initi
                            double eps, int max_sweeps, double *svf, const double *e_features,
                            int ef_shared, double *grad, int32_t *n_iter, int32_t *status, int mode,
                            void *stream) {
+    return irlb200_svf_ordered(t, B, p_initial, p0_shared, terminal_mask, mask_shared, policy, eps, max_sweeps, svf,
+                               e_features, ef_shared, grad, n_iter, status, mode, nullptr, stream);
+}
+
+extern "C" int irlb200_svf_ordered(const irlb200_tables *t, int B, const double *p_initial, int p0_shared,
+                                   const uint8_t *terminal_mask, int mask_shared, const double *policy,
+                                   double eps, int max_sweeps, double *svf, const double *e_features,
+                                   int ef_shared, double *grad, int32_t *n_iter, int32_t *status, int mode,
+                                   const int32_t *order, void *stream) {
     if (int rc = check_tables(t, false, true)) return rc;
     if (B <= 0 || !p_initial || !terminal_mask || !policy || !svf) return fail(IRLB200_EINVAL, "svf: bad argument");
     if (grad && !e_features) return fail(IRLB200_EINVAL, "svf: grad requested without e_features");
@@ -685,6 +694,7 @@ extern "C" int irlb200_svf(const irlb200_tables *t, int B, const double *p_initi
     bt.term_stride = mask_shared ? 0 : (size_t)t->S;
     bt.ef_stride = ef_shared ? 0 : (size_t)t->S;
     bt.n_iter = n_iter; bt.status = status; bt.out_stride = 1;
+    bt.order = (!want_cluster && mode == IRLB200_MODE_CTA) ? order : nullptr;   // one-CTA-per-problem launches only
     if (want_cluster) {
         if (device_count_impl() <= 0) return fail(IRLB200_ECUDA, "no CUDA device");
         int rc = launch_svf_cluster(bt, B, t->stencil_n, cl_size, (cudaStream_t)stream);

@@ -250,11 +250,17 @@ class PeerSlabGrid(SlabGrid):
     ghost-row exchange of the policy before the forward pass, and a process-group barrier
     around each launch.  CUDA only."""
 
-    def __init__(self, size, p_slip=0.2, icy=True, group=None, timeout_s=20.0, overlap=True):
+    def __init__(self, size, p_slip=0.2, icy=True, group=None, timeout_s=20.0, overlap=True, flow=True,
+                 chunk_sweeps=0):
         super().__init__(size, p_slip, icy, group=group, backend=CudaBackend())
         import os
         # boundary-first kernel: halo exchange overlaps the interior sweep (IRLB200_SLAB_OVERLAP=0/1 overrides)
         self.overlap = int(os.environ.get("IRLB200_SLAB_OVERLAP", "1" if overlap else "0"))
+        # dataflow kernel (csrc/slab_flow.cu): neighbour flags instead of a barrier per sweep; the default.
+        # IRLB200_SLAB_FLOW=0 selects the barrier-per-sweep kernels (cross-check variant)
+        self.flow = int(os.environ.get("IRLB200_SLAB_FLOW", "1" if flow else "0"))
+        self.chunk_sweeps = int(chunk_sweeps)
+        self._work = None
         import ctypes
         E = self.backend.E
         self.E, self.ct = E, ctypes
@@ -311,11 +317,22 @@ class PeerSlabGrid(SlabGrid):
         self._fence()
         ms = E.DEFAULT_MAX_SWEEPS if max_sweeps is None else int(max_sweeps)
         with E._timed("slab_persistent"):
-            E._check(E._lib.irlb200_slab_persistent(
-                op, self.rank, self.world, self._blocks, self.n_states, self.lo, self.cnt, self.halo, self.A, self.K,
-                E._ptr(idx), E._ptr(p), E._ptr(c0), E._ptr(c1), E._ptr(policy_in), E._ptr(mask), E._ptr(w_scratch),
-                float(discount), float(eps), ms, int(vi_mean), E._ptr(out), E._ptr(policy_out), E._ptr(n_iter),
-                E._ptr(status), self.timeout_s, int(self.overlap), E._stream()))
+            if self.flow:
+                if self._work is None:
+                    nbytes = int(E._lib.irlb200_slab_flow_work_bytes(self.cnt))
+                    self._work = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                E._check(E._lib.irlb200_slab_flow(
+                    op, self.rank, self.world, self._blocks, self.n_states, self.lo, self.cnt, self.halo, self.A,
+                    self.K, E._ptr(idx), E._ptr(p), E._ptr(c0), E._ptr(c1), E._ptr(policy_in), E._ptr(mask),
+                    E._ptr(w_scratch), float(discount), float(eps), ms, int(vi_mean), E._ptr(out), E._ptr(policy_out),
+                    E._ptr(n_iter), E._ptr(status), self.timeout_s, self.chunk_sweeps, E._ptr(self._work),
+                    self._work.numel(), E._stream()))
+            else:
+                E._check(E._lib.irlb200_slab_persistent(
+                    op, self.rank, self.world, self._blocks, self.n_states, self.lo, self.cnt, self.halo, self.A,
+                    self.K, E._ptr(idx), E._ptr(p), E._ptr(c0), E._ptr(c1), E._ptr(policy_in), E._ptr(mask),
+                    E._ptr(w_scratch), float(discount), float(eps), ms, int(vi_mean), E._ptr(out), E._ptr(policy_out),
+                    E._ptr(n_iter), E._ptr(status), self.timeout_s, int(self.overlap), E._stream()))
         torch.cuda.synchronize()
         self.last_n_iter, self.last_status = int(n_iter.item()), int(status.item())
         if self.last_status == ST_ABORTED:

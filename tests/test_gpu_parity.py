@@ -495,13 +495,14 @@ def test_slab_single_rank_matches_engine_and_oracle():
     close(val, vref)
 
 
-def test_peer_slab_single_rank():
-    """The persistent slab kernel (in-kernel barrier / vote path) with one rank: same results and
-    sweep counts as the oracle and bitwise the same as the single-GPU engine."""
+@pytest.mark.parametrize("flow", [True, False])
+def test_peer_slab_single_rank(flow):
+    """The persistent slab kernels (flow: neighbour flags + chunked stop rule; else: barrier per sweep)
+    with one rank: same results and sweep counts as the oracle and bitwise the same as the single-GPU engine."""
     import slab
     n = 16
     S = n * n
-    g = slab.PeerSlabGrid(n, 0.2, icy=True)
+    g = slab.PeerSlabGrid(n, 0.2, icy=True, flow=flow)
     try:
         r = np.full(S, -0.1); r[S - 1] = 1.0
         phi = np.full(S, -np.inf); phi[S - 1] = 0.0
@@ -526,6 +527,80 @@ def test_peer_slab_single_rank():
         assert g.last_n_iter == 25 and g.last_status == E.ST_MAXSWEEPS
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("n,chunk,blocks", [(16, 1, 0), (16, 7, 0), (64, 32, 0), (64, 64, 3), (64, 5, 16),
+                                            (200, 32, 0), (200, 13, 37), (96, 64, 1)])
+def test_slab_flow_kernel_is_bitwise_the_barrier_kernel(n, chunk, blocks, monkeypatch):
+    """Dataflow slab kernel (csrc/slab_flow.cu: neighbour progress flags, stop rule all-reduced once per
+    chunk, snapshot + replay) against the barrier-per-sweep slab kernel and the single-GPU cooperative
+    grid kernel: identical sweep counts and bitwise identical soft-VI policy / value, VI value and
+    forward SVF for every chunk length and CTA count (stop inside a chunk, on its last sweep, guard hit
+    inside / on the edge of a chunk)."""
+    import slab
+    if blocks:
+        monkeypatch.setenv("IRLB200_FLOW_BLOCKS", str(blocks))
+    S = n * n
+    rng = np.random.default_rng(n + chunk)
+    r = -0.1 + 0.02 * rng.standard_normal(S); r[S - 1] = 1.0
+    phi = np.full(S, -np.inf); phi[S - 1] = 0.0
+    p0 = np.zeros(S); p0[0] = 0.7; p0[S // 2] = 0.3
+    gf = slab.PeerSlabGrid(n, 0.2, icy=True, flow=True, chunk_sweeps=chunk)
+    gb = slab.PeerSlabGrid(n, 0.2, icy=True, flow=False)
+    try:
+        pol_f, v_f = gf.soft_vi(r, phi, 0.9, 1e-5)
+        n_f = gf.last_n_iter
+        pol_b, v_b = gb.soft_vi(r, phi, 0.9, 1e-5)
+        assert n_f == gb.last_n_iter and gf.last_status == 0
+        assert (pol_f == pol_b).all() and (v_f == v_b).all()
+        t = E.gridworld_tables(n, 0.2, slots=4)
+        pol_e = E.soft_vi(t, E.terminal_phi([S - 1], S), r, 0.9, mode=E.MODE_GRID)
+        assert counts()[0] == n_f and (pol_e[0] == pol_f).all()
+        # forward pass: to convergence at the small sizes, otherwise budgets around the chunk edges
+        budgets = [None] if n <= 16 else [1, chunk, chunk + 1, 3 * chunk - 1, 257]
+        for ms in budgets:
+            d_f = gf.svf(p0, [S - 1], pol_f, 1e-5, max_sweeps=ms)
+            nf, sf = gf.last_n_iter, gf.last_status
+            d_b = gb.svf(p0, [S - 1], pol_f, 1e-5, max_sweeps=ms)
+            assert (nf, sf) == (gb.last_n_iter, gb.last_status), (ms, nf, sf, gb.last_n_iter, gb.last_status)
+            assert (d_f == d_b).all(), ms
+        val_f = gf.value_iteration(r, 0.95, 1e-4)
+        nv = gf.last_n_iter
+        val_b = gb.value_iteration(r, 0.95, 1e-4)
+        assert nv == gb.last_n_iter and (val_f == val_b).all()
+        # NaN ends the loop at the sweep in which it first shows (status NONFINITE), like the reference
+        rn = r.copy(); rn[S // 3] = np.nan
+        val_f = gf.value_iteration(rn, 0.95, 1e-4)
+        nf, sf = gf.last_n_iter, gf.last_status
+        val_b = gb.value_iteration(rn, 0.95, 1e-4)
+        assert (nf, sf) == (gb.last_n_iter, gb.last_status) and sf == E.ST_NONFINITE
+    finally:
+        gf.close()
+        gb.close()
+
+
+def test_launch_order_hint_does_not_change_results():
+    """Longest-first launch order of a batch (irlb200_svf_ordered): a scheduling hint only."""
+    import torch
+    n, B = 16, 300
+    S = n * n
+    tabs = E.gridworld_tables(n, 0.1 + 0.2 * np.arange(B) / B)
+    rng = np.random.default_rng(3)
+    r = -np.log(4.0) + 0.01 * rng.standard_normal((B, S))
+    p0 = np.zeros(S); p0[0] = 1.0
+    mask = E.terminal_mask([S - 1], S)
+    pol = E.backward(tabs, mask, r)
+    d0 = E.svf(tabs, p0, mask, pol, 1e-5, order=None)
+    n0 = counts().copy()
+    assert getattr(tabs, "_svf_order", None) is None
+    perm = torch.randperm(B, device=d0.device).to(torch.int32)
+    d1, g1 = E.svf(tabs, p0, mask, pol, 1e-5, e_features=np.zeros(S), order=perm)
+    assert (d1 == d0).all() and (counts() == n0).all() and (g1 == -d0).all()
+    d2 = E.svf(tabs, p0, mask, pol, 1e-5)                       # "auto": records the order for the next call
+    hint = tabs._svf_order.cpu().numpy()
+    assert sorted(hint.tolist()) == list(range(B)) and (np.diff(n0[hint]) <= 0).all()
+    d3 = E.svf(tabs, p0, mask, pol, 1e-5)                       # uses it
+    assert (d2 == d0).all() and (d3 == d0).all() and (counts() == n0).all()
 
 
 @pytest.mark.parametrize("n,streamed", [(48, "0"), (48, "1"), (200, "0"), (200, "1")])
