@@ -271,14 +271,21 @@ int    irlb200_slab_persistent(int op, int rank, int world, void *const *blocks,
                                int32_t *n_iter, int32_t *status, double timeout_s, int overlap,
                                void *stream);
 
-/* Slab mode without a per-sweep barrier (csrc/slab_flow.cu): same arguments, blocks, header and
- * results as irlb200_slab_persistent, but every persistent CTA owns a fixed range of states and waits
- * only for the CTAs (and, on the slab's first / last grid row, the neighbouring GPU) within one grid
- * row of it; the stop rule is all-reduced once per `chunk` sweeps (<= 64; <= 0: default 32) and the
+/* Slab mode without a per-sweep barrier (csrc/slab_flow.cu): same arguments and results as
+ * irlb200_slab_persistent (blocks of irlb200_slab_flow_block_bytes bytes), but every persistent CTA
+ * owns a fixed range of states and waits only for the CTAs (and, on the slab's first / last grid
+ * row, the neighbouring GPU's mailbox) within one grid row of it; the stop rule is all-reduced once per `chunk` sweeps (<= 64; <= 0: default 32) and the
  * exact stopping sweep of the reference (maxent.py:108,326; solver.py:40) is reproduced by
  * snapshot-and-replay inside the kernel.  `work` is a caller-owned device buffer of at least
  * irlb200_slab_flow_work_bytes(cnt) bytes, private to this call (not peer-mapped; any contents). */
 size_t irlb200_slab_flow_work_bytes(int cnt);
+/* The peer-mapped block of a rank for irlb200_slab_flow is the block of irlb200_slab_persistent followed by
+ * "LL" mailboxes for one ghost row (halo states) from each neighbour: boundary-row values cross NVLink as
+ * two 8-byte words carrying half the value and the iterate number each, so data and arrival are one one-way
+ * store (no system-scope fence, no flag).  irlb200_slab_flow_reset zeroes header and mailboxes (all ranks,
+ * before any rank launches); the block also serves irlb200_slab_persistent. */
+size_t irlb200_slab_flow_block_bytes(int S_total, int halo);
+int    irlb200_slab_flow_reset(void *block, int S_total, int halo, void *stream);
 int    irlb200_slab_flow(int op, int rank, int world, void *const *blocks, int S_total, int lo, int cnt,
                          int halo, int A, int K, const int32_t *idx, const double *p, const double *c0,
                          const double *c1, const double *policy_in, const uint8_t *terminal_mask,

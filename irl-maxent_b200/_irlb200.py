@@ -68,6 +68,8 @@ SIGNATURES = {
     "irlb200_slab_persistent": ([_i, _i, _i, ctypes.POINTER(ctypes.c_void_p), _i, _i, _i, _i, _i, _i, _vp, _vp, _vp,
                                  _vp, _vp, _vp, _vp, _d, _d, _i, _i, _vp, _vp, _vp, _vp, _d, _i, _vp], _i),
     "irlb200_slab_flow_work_bytes": ([_i], ctypes.c_size_t),
+    "irlb200_slab_flow_block_bytes": ([_i, _i], ctypes.c_size_t),
+    "irlb200_slab_flow_reset": ([_vp, _i, _i, _vp], _i),
     "irlb200_slab_flow": ([_i, _i, _i, ctypes.POINTER(ctypes.c_void_p), _i, _i, _i, _i, _i, _i, _vp, _vp, _vp,
                            _vp, _vp, _vp, _vp, _d, _d, _i, _i, _vp, _vp, _vp, _vp, _d, _i, _vp, ctypes.c_size_t,
                            _vp], _i),

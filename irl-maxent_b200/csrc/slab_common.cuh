@@ -63,21 +63,48 @@ struct OverlapArgs {
     double *out, *policy_out;
 };
 
-template <int OP, int A_T, int K_T>
-__device__ __forceinline__ double overlap_update(const OverlapArgs &a, const double *x_in, int i, double *q) {
+// one state's update with the iterate read through `xl(global index)`
+template <int OP, int A_T, int K_T, class XL>
+__device__ __forceinline__ double slab_update(const OverlapArgs &a, XL xl, int i, double *q) {
     const int A = A_T > 0 ? A_T : a.A, K = K_T > 0 ? K_T : a.K;
     if (OP == 3) {
         double acc = 0.0;
 #pragma unroll
         for (int j = 0; j < K; ++j)
-            acc = fma(__ldg(a.w + (size_t)j * a.cnt + i), ld_cg(x_in + __ldg(a.idx + (size_t)j * a.cnt + i)), acc);
+            acc = fma(__ldg(a.w + (size_t)j * a.cnt + i), xl(__ldg(a.idx + (size_t)j * a.cnt + i)), acc);
         return __ldg(a.c0 + i) + acc;
     }
     const double k1 = (OP == kOpSoftVI) ? a.c1[i] : 0.0;
     return succ_update<OP, A_T>(
         A, K, [&](int aa, int j) { return __ldg(a.p + ((size_t)aa * K + j) * a.cnt + i); },
-        [&](int j) { return ld_cg(x_in + __ldg(a.idx + (size_t)j * a.cnt + i)); }, a.c0[i], k1, a.discount,
+        [&](int j) { return xl(__ldg(a.idx + (size_t)j * a.cnt + i)); }, a.c0[i], k1, a.discount,
         a.vi_mean, q);
+}
+
+template <int OP, int A_T, int K_T>
+__device__ __forceinline__ double overlap_update(const OverlapArgs &a, const double *x_in, int i, double *q) {
+    return slab_update<OP, A_T, K_T>(a, [&](int g) { return ld_cg(x_in + g); }, i, q);
+}
+
+// ---------------------------------------------------------------------------
+// "LL" mailbox slots for boundary rows that cross GPUs (slab_flow.cu): a double travels as two 8-byte
+// words, each carrying 32 bits of the value and a 32-bit tag (the iterate number + 1).  8-byte stores
+// are single-copy atomic over NVLink, so a reader that finds the expected tag in BOTH words has the
+// value -- data and "it has arrived" in one one-way flight, no fence and no separate flag.
+// ---------------------------------------------------------------------------
+struct __align__(16) LLSlot { unsigned long long w[2]; };
+
+__device__ __forceinline__ void ll_write(LLSlot *p, double v, unsigned tag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v), t = (unsigned long long)tag << 32;
+    const unsigned long long w0 = (b & 0xffffffffull) | t, w1 = (b >> 32) | t;
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ bool ll_try_read(const LLSlot *p, unsigned tag, double &v) {
+    unsigned long long w0, w1;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+    if ((unsigned)(w0 >> 32) != tag || (unsigned)(w1 >> 32) != tag) return false;
+    v = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+    return true;
 }
 
 }  // namespace irlb200

@@ -7,15 +7,18 @@
 // grid row away, so nothing in the arithmetic needs that:
 //
 //   * every persistent CTA owns a FIXED contiguous range of the slab's states and publishes, after
-//     each sweep, one progress word (release store).  Before sweep k it waits only for the few CTAs
-//     whose ranges lie within one grid row of its own to have finished sweep k-1 -- which is both
-//     the read-after-write condition (their rows are my halo) and the write-after-read condition
-//     (they have finished reading the buffer I am about to overwrite).  CTAs of one SM drift apart
-//     by a fraction of a sweep, so one CTA's wait is hidden behind another's loads;
-//   * across GPUs the same rule holds between the CTAs that own the first / last grid row of
-//     neighbouring slabs: they push their row into the neighbour's ghost row with NVLink peer
-//     stores, fence at system scope, count themselves on a local counter, and the last one raises
-//     ONE data flag in the neighbour's header.  No all-to-all, no collective call;
+//     each sweep, one progress word.  Before sweep k it waits only for the few CTAs whose ranges lie
+//     within one grid row of its own to have finished sweep k-1 -- which is both the
+//     read-after-write condition (their rows are my halo) and the write-after-read condition (they
+//     have finished reading the buffer I am about to overwrite).  CTAs of one SM drift apart by a
+//     fraction of a sweep, so one CTA's wait is hidden behind another's loads;
+//   * across GPUs the boundary rows travel through "LL" mailboxes (slab_common.cuh): the CTAs that
+//     own the first / last grid row of a slab store every new value straight into the neighbouring
+//     GPU's mailbox as two 8-byte words that each carry half the value and the iterate number.  The
+//     consumer spins on the words it needs until both tags match: data and arrival in ONE one-way
+//     NVLink flight -- no system-scope fence, no flag, no collective call on the sweep path.  Those
+//     rows get their own small CTAs (about one state per thread), so the flight runs while the
+//     interior CTAs are still sweeping;
 //   * the stop rule (`while delta > eps`, maxent.py:108,326; solver.py:40) needs the maximum over
 //     ALL states, but not immediately: every CTA records one vote bit per sweep, and only every
 //     `chunk` sweeps the masks are OR-ed over the GPU and exchanged between the ranks behind one
@@ -36,10 +39,8 @@
 namespace irlb200 {
 
 struct FlowShared {                               // at byte kFlowOffset of every rank's peer-mapped header
-    unsigned long long gflag[2];                  // [0]: rank-1's last row, [1]: rank+1's first row complete through v-1 sweeps
-    unsigned long long bcount[2];                 // local: low / high boundary CTAs that published, monotonic
     unsigned long long abort;                     // != 0: somebody timed out
-    unsigned long long pad[3];
+    unsigned long long pad[7];
     unsigned long long vgt[2], vnan[2];           // vote masks of the current chunk (bit i = sweep i), by barrier parity
     unsigned long long rel_gt[4], rel_nan[4];     // decision masks broadcast with the barrier release
     unsigned long long xgt[2][kMaxRanks], xnan[2][kMaxRanks];   // masks received from the other ranks
@@ -49,12 +50,20 @@ static_assert(sizeof(SlabShared) <= kFlowOffset, "SlabShared grew into the flow 
 static_assert(kFlowOffset + sizeof(FlowShared) <= kSlabHeaderBytes, "flow header does not fit");
 constexpr int kProgressStride = 4;                // progress words 32 bytes apart (one sector each)
 
+// block of a rank: [header | iterate 0 [S_total] | iterate 1 [S_total] | mailboxes [2 sides][2 parities][halo]]
+__host__ __device__ inline size_t flow_mail_offset(int S_total) {
+    return (kSlabHeaderBytes + 2 * sizeof(double) * (size_t)S_total + 255) & ~(size_t)255;
+}
+
 __device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v) {
     *(volatile unsigned long long *)p = v;
 }
 
-template <int OP, int A_T, int K_T>
-__global__ void __launch_bounds__(256, OP == 3 ? 4 : 3)
+// U > 1 (forward pass, compile-time K): a thread works on U of its states at a time -- all their table
+// rows are requested first, then all gathers, so a sweep over ~3.5 states per thread (2048 x 2048 on
+// 8 GPUs) is one or two rounds of dependent L2 accesses instead of 3.5.
+template <int OP, int A_T, int K_T, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB)
     slab_flow_kernel(const OverlapArgs a, const SlabPeers pe, unsigned char *base, unsigned long long *progress,
                      double *snap, const int chunk, const int edge, int32_t *n_iter, int32_t *status) {
     __shared__ unsigned long long s_gt, s_nanmask;
@@ -64,16 +73,21 @@ __global__ void __launch_bounds__(256, OP == 3 ? 4 : 3)
     FlowShared *fs = reinterpret_cast<FlowShared *>(base + kFlowOffset);
     double *buf0 = reinterpret_cast<double *>(base + kSlabHeaderBytes), *buf1 = buf0 + a.S_total;
     const int tid = threadIdx.x, cta = blockIdx.x, nthr = blockDim.x, nb = gridDim.x;
-    const int G = pe.world, me = pe.rank, lo = a.lo, cnt = a.cnt, h = a.halo;
-    const bool has_lo = pe.lo_buf0 != nullptr, has_hi = pe.hi_buf0 != nullptr;
+    const int G = pe.world, me = pe.rank, lo = a.lo, cnt = a.cnt, h = a.halo, hi = a.lo + a.cnt;
+    const bool has_lo = me > 0, has_hi = me < G - 1;
     const int A = A_T > 0 ? A_T : a.A, K = K_T > 0 ? K_T : a.K;
+    // mailboxes: mine (what the neighbours send me) and theirs (where my boundary rows go)
+    const size_t mo = flow_mail_offset(a.S_total);
+    LLSlot *my_mail = reinterpret_cast<LLSlot *>(base + mo);                       // [side 0: from rank-1 | side 1: from rank+1][parity][h]
+    LLSlot *to_lo = has_lo ? reinterpret_cast<LLSlot *>(reinterpret_cast<unsigned char *>(pe.shared[me - 1]) + mo) + (size_t)2 * h : nullptr;
+    LLSlot *to_hi = has_hi ? reinterpret_cast<LLSlot *>(reinterpret_cast<unsigned char *>(pe.shared[me + 1]) + mo) : nullptr;
 
     // ---- fixed ownership and the dependence set ----------------------------------------------
     // Three zones of contiguous, near-equal ranges: the slab's first grid row (when rank-1 exists) is split
     // over `edge` CTAs, its last row (when rank+1 exists) over another `edge`, the interior over the rest.
     // About one state per thread on the edge rows: their CTAs finish a sweep in a fraction of the time the
-    // interior CTAs need, so the NVLink flight of the boundary row (system fence + flag, ~3 us) runs
-    // while the interior is still being swept instead of adding to every sweep.  edge == 0: uniform split.
+    // interior CTAs need, so the NVLink flight of the boundary row runs while the interior is still being
+    // swept instead of adding to every sweep.  edge == 0: uniform split.
     const int eL = has_lo ? edge : 0, eH = has_hi ? edge : 0, mid = nb - eL - eH;
     const int z0 = eL ? h : 0, z1 = eH ? cnt - h : cnt;
     auto ceil_div = [](long long x, long long y) { return (int)((x + y - 1) / y); };
@@ -89,12 +103,8 @@ __global__ void __launch_bounds__(256, OP == 3 ? 4 : 3)
     };
     const int beg = beg_of(cta), end = beg_of(cta + 1);
     const int d_lo = cta_of(max(beg - h, 0)), d_hi = cta_of(min(end + h, cnt) - 1);
-    const bool low_push = has_lo && beg < h;                  // owns part of the first grid row: pushes to rank-1, reads its ghosts
-    const bool high_push = has_hi && end > cnt - h;
-    const unsigned long long m_lo = (unsigned long long)cta_of(min(h, cnt) - 1) + 1ull;        // CTAs with beg < h
-    const unsigned long long m_hi = (unsigned long long)(nb - cta_of(max(cnt - h, 0)));        // CTAs with end > cnt - h
-    FlowShared *fs_lo = has_lo ? reinterpret_cast<FlowShared *>(reinterpret_cast<unsigned char *>(pe.shared[me - 1]) + kFlowOffset) : nullptr;
-    FlowShared *fs_hi = has_hi ? reinterpret_cast<FlowShared *>(reinterpret_cast<unsigned char *>(pe.shared[me + 1]) + kFlowOffset) : nullptr;
+    // within one grid row of the neighbouring slab: reads its boundary row from the mailbox
+    const bool near_lo = has_lo && beg < h, near_hi = has_hi && end > cnt - h;
 
     unsigned seq = 0;                  // full-barrier sequence number
     bool dead = false;
@@ -105,33 +115,44 @@ __global__ void __launch_bounds__(256, OP == 3 ? 4 : 3)
             if (r != me)
                 st_volatile_u64(&reinterpret_cast<FlowShared *>(reinterpret_cast<unsigned char *>(pe.shared[r]) + kFlowOffset)->abort, 1ull);
     };
+    // slow path of every spin loop (every 1024 polls): false = give up
+    auto keep_waiting = [&](unsigned long long &t0) -> bool {
+        if (*(volatile unsigned long long *)&fs->abort) return false;
+        const unsigned long long now = globaltimer_ns();
+        if (!t0) t0 = now;
+        else if ((long long)(now - t0) > pe.timeout_ns) { raise_abort(); return false; }
+        return true;
+    };
     // wait until *p >= want (monotonic words); false = aborted / timed out
     auto spin_ge = [&](const unsigned long long *p, unsigned long long want, bool sys) -> bool {
         unsigned long long t0 = 0ull;
         for (unsigned spins = 0;; ++spins) {
             const unsigned long long v = sys ? ld_acquire_sys(p) : ld_acquire_gpu(p);
             if (v >= want) return true;
-            if ((spins & 1023u) == 1023u) {
-                if (*(volatile unsigned long long *)&fs->abort) return false;
-                const unsigned long long now = globaltimer_ns();
-                if (!t0) t0 = now;
-                else if ((long long)(now - t0) > pe.timeout_ns) { raise_abort(); return false; }
-            }
+            if ((spins & 1023u) == 1023u && !keep_waiting(t0)) return false;
         }
     };
-    // value of an owned state: local store, plus the neighbour's ghost row for boundary states
-    auto put = [&](int b, int i, double v) {
-        const int g = lo + i;
-        st_cg((b ? buf1 : buf0) + g, v);
-        if (has_lo && i < h) st_cg((b ? pe.lo_buf1 : pe.lo_buf0) + g, v);
-        if (has_hi && i >= cnt - h) st_cg((b ? pe.hi_buf1 : pe.hi_buf0) + g, v);
+    // iterate number `it` (buffer it & 1, mailbox tag it + 1) at global index g
+    auto load_x = [&](const double *x_in, unsigned it, int g) -> double {
+        if (g >= lo && g < hi) return ld_cg(x_in + g);
+        const LLSlot *slot = g < lo ? my_mail + (size_t)(it & 1u) * h + (g - (lo - h))
+                                    : my_mail + (size_t)(2u + (it & 1u)) * h + (g - hi);
+        double v = 0.0;
+        unsigned long long t0 = 0ull;
+        for (unsigned spins = 0; !ll_try_read(slot, it + 1u, v); ++spins)
+            if ((spins & 1023u) == 1023u && !keep_waiting(t0)) { s_dead = 1; break; }
+        return v;
+    };
+    // iterate number `it` of an owned state: local store, plus the neighbour's mailbox for boundary rows
+    auto put = [&](unsigned it, int i, double v) {
+        st_cg(((it & 1u) ? buf1 : buf0) + lo + i, v);
+        if (has_lo && i < h) ll_write(to_lo + (size_t)(it & 1u) * h + i, v, it + 1u);
+        if (has_hi && i >= cnt - h) ll_write(to_hi + (size_t)(it & 1u) * h + (i - (cnt - h)), v, it + 1u);
     };
     // thread 0, after a bar.sync that covers the CTA's stores: "my rows hold iterate number v - 1"
     auto publish = [&](unsigned long long v) {
-        if (low_push || high_push) __threadfence_system(); else __threadfence();
+        __threadfence();
         st_volatile_u64(progress + (size_t)cta * kProgressStride, v);
-        if (low_push && atomicAdd(&fs->bcount[0], 1ull) + 1ull == v * m_lo) st_volatile_u64(&fs_lo->gflag[1], v);
-        if (high_push && atomicAdd(&fs->bcount[1], 1ull) + 1ull == v * m_hi) st_volatile_u64(&fs_hi->gflag[0], v);
     };
 
     // Full barrier over all CTAs of all ranks (once per chunk, not per sweep): local arrival counter, the
@@ -145,7 +166,7 @@ __global__ void __launch_bounds__(256, OP == 3 ? 4 : 3)
             const unsigned long long want = (unsigned long long)(seq + 1u);
             if (my_gt) atomicOr(&fs->vgt[par], my_gt);
             if (my_nan) atomicOr(&fs->vnan[par], my_nan);
-            if (low_push || high_push) __threadfence_system(); else __threadfence();   // restored rows reach the peers too
+            __threadfence();
             const unsigned long long old = atomicAdd(&sh->slot[s4], 1ull);
             if (old == (unsigned long long)nb - 1ull) {
                 __threadfence();
@@ -153,7 +174,7 @@ __global__ void __launch_bounds__(256, OP == 3 ? 4 : 3)
                 unsigned long long mn = *(volatile unsigned long long *)&fs->vnan[par];
                 fs->vgt[par] = 0ull;                         // next use: two barriers from now
                 fs->vnan[par] = 0ull;
-                bool ok = !dead;
+                bool ok = !dead && !s_dead;
                 if (G > 1 && ok) {
                     for (int r = 0; r < G; ++r) {
                         if (r == me) continue;
@@ -161,7 +182,7 @@ __global__ void __launch_bounds__(256, OP == 3 ? 4 : 3)
                         st_volatile_u64(&fr->xgt[par][me], mg);
                         st_volatile_u64(&fr->xnan[par][me], mn);
                     }
-                    __threadfence_system();                  // masks (and restored rows) before the flags
+                    __threadfence_system();                  // masks before the flags
                     for (int r = 0; r < G; ++r)
                         if (r != me) st_volatile_u64(&pe.shared[r]->flags[par][me], want);
                     for (int r = 0; r < G && ok; ++r) {
@@ -190,7 +211,7 @@ __global__ void __launch_bounds__(256, OP == 3 ? 4 : 3)
             }
             s_gt = *(volatile unsigned long long *)&fs->rel_gt[s4];
             s_nanmask = *(volatile unsigned long long *)&fs->rel_nan[s4];
-            s_dead = (rel & 4ull) ? 1 : 0;
+            if (rel & 4ull) s_dead = 1;
         }
         __syncthreads();
         all_gt = s_gt;
@@ -202,6 +223,7 @@ __global__ void __launch_bounds__(256, OP == 3 ? 4 : 3)
 
     // ---- prologue: weights (forward pass), initial iterate -------------------------------------
     if (tid == 0) { s_nan = 0; s_dead = 0; }
+    __syncthreads();
     for (int i = beg + tid; i < end; i += nthr) {
         if (OP == 3) {
             for (int j = 0; j < K; ++j) {
@@ -212,7 +234,7 @@ __global__ void __launch_bounds__(256, OP == 3 ? 4 : 3)
                 a.w[(size_t)j * cnt + i] = a.term[pred] ? 0.0 : acc;
             }
         }
-        put(0, i, OP == kOpSoftVI ? kNegHuge : 0.0);
+        put(0u, i, OP == kOpSoftVI ? kNegHuge : 0.0);
     }
     __syncthreads();
     if (tid == 0) publish(1ull);
@@ -223,23 +245,63 @@ __global__ void __launch_bounds__(256, OP == 3 ? 4 : 3)
         const unsigned long long need = (unsigned long long)q + 1ull;
         for (int d = d_lo + tid; d <= d_hi; d += nthr)
             if (d != cta) ok = spin_ge(progress + (size_t)d * kProgressStride, need, false) && ok;
-        if (low_push && tid == nthr - 1) ok = spin_ge(&fs->gflag[0], need, true) && ok;
-        if (high_push && tid == nthr - 2) ok = spin_ge(&fs->gflag[1], need, true) && ok;
         if (__syncthreads_or(ok ? 0 : 1)) return false;
         const double *x_in = (q & 1u) ? buf1 : buf0;
-        const int bo = (int)((q + 1u) & 1u);
         bool gt = false, nan = false;
-        for (int i = beg + tid; i < end; i += nthr) {
-            const double x = overlap_update<OP, A_T, K_T>(a, x_in, i, nullptr);
-            const double xo = ld_cg(x_in + lo + i);
-            const double diff = fabs(x - xo);
-            gt |= diff > a.eps;
-            nan |= diff != diff;
-            if (take_snap) snap[i] = xo;
-            put(bo, i, x);
-        }
+        auto body = [&](auto xl) {
+            if (OP == 3 && K_T > 0 && U > 1) {
+                constexpr int KK = K_T > 0 ? K_T : 1, UU = U > 0 ? U : 1;
+                for (int i0 = beg + tid; i0 < end; i0 += UU * nthr) {
+                    int ix[UU][KK];
+                    double wv[UU][KK], p0v[UU], xo[UU], xv[UU][KK];
+#pragma unroll
+                    for (int u = 0; u < UU; ++u) {
+                        const int i = min(i0 + u * nthr, end - 1);      // clamped: inactive slots repeat a valid state
+#pragma unroll
+                        for (int j = 0; j < KK; ++j) {
+                            ix[u][j] = __ldg(a.idx + (size_t)j * cnt + i);
+                            wv[u][j] = __ldg(a.w + (size_t)j * cnt + i);
+                        }
+                        p0v[u] = __ldg(a.c0 + i);
+                        xo[u] = ld_cg(x_in + lo + i);
+                    }
+#pragma unroll
+                    for (int u = 0; u < UU; ++u)
+#pragma unroll
+                        for (int j = 0; j < KK; ++j) xv[u][j] = xl(ix[u][j]);
+#pragma unroll
+                    for (int u = 0; u < UU; ++u) {
+                        const int i = i0 + u * nthr;
+                        if (i < end) {
+                            double acc = 0.0;
+#pragma unroll
+                            for (int j = 0; j < KK; ++j) acc = fma(wv[u][j], xv[u][j], acc);   // same chain as slab_update
+                            const double x = p0v[u] + acc;
+                            const double diff = fabs(x - xo[u]);
+                            gt |= diff > a.eps;
+                            nan |= diff != diff;
+                            if (take_snap) snap[i] = xo[u];
+                            put(q + 1u, i, x);
+                        }
+                    }
+                }
+            } else {
+                for (int i = beg + tid; i < end; i += nthr) {
+                    const double x = slab_update<OP, A_T, K_T>(a, xl, i, nullptr);
+                    const double xo = ld_cg(x_in + lo + i);
+                    const double diff = fabs(x - xo);
+                    gt |= diff > a.eps;
+                    nan |= diff != diff;
+                    if (take_snap) snap[i] = xo;
+                    put(q + 1u, i, x);
+                }
+            }
+        };
+        if (near_lo || near_hi) body([&](int g) { return load_x(x_in, q, g); });
+        else body([&](int g) { return ld_cg(x_in + g); });
         if (nan) s_nan = 1;
         const int any = __syncthreads_or(gt ? 1 : 0);
+        if (s_dead) return false;
         if (tid == 0) {
             publish((unsigned long long)q + 2ull);
             any_gt = any != 0;
@@ -280,9 +342,13 @@ __global__ void __launch_bounds__(256, OP == 3 ? 4 : 3)
         const int stop = __ffsll((long long)ends) - 1;
         st = ((all_nan >> stop) & 1ull) ? IRLB200_ST_NONFINITE : IRLB200_ST_CONVERGED;
         if (stop == k - 1) { n += k; break; }                 // ended on the chunk's last sweep: nothing to undo
-        // restore the iterate the chunk started from and replay sweeps 0..stop
-        for (int i = beg + tid; i < end; i += nthr) put((int)(q & 1u), i, snap[i]);
-        if (!full_barrier(0ull, 0ull, all_gt, all_nan)) { st = IRLB200_ST_ABORTED; break; }
+        // Restore the iterate the chunk started from and replay sweeps 0..stop.  The iterate number jumps
+        // by 2 (same buffer parity) so that the mailbox tags of the restored rows differ from the tags
+        // of the rows they replace; everybody is behind the barrier above, the progress words order the rest.
+        q += 2u;
+        for (int i = beg + tid; i < end; i += nthr) put(q, i, snap[i]);
+        __syncthreads();
+        if (tid == 0) publish((unsigned long long)q + 1ull);
         for (int i = 0; i <= stop && ok; ++i) {
             bool g, nn;
             ok = sweep(q, false, g, nn);
@@ -300,7 +366,7 @@ __global__ void __launch_bounds__(256, OP == 3 ? 4 : 3)
             a.out[i] = ld_cg(x_new + lo + i);
             if (OP == kOpSoftVI && a.policy_out && q > 0) {
                 double qv[QN];
-                const double x = overlap_update<OP, A_T, K_T>(a, x_old, i, qv);
+                const double x = slab_update<OP, A_T, K_T>(a, [&](int g) { return load_x(x_old, q - 1u, g); }, i, qv);
                 for (int aa = 0; aa < A; ++aa) a.policy_out[(size_t)i * A + aa] = exp(qv[aa] - x);     // maxent.py:341
             }
         }
@@ -328,6 +394,22 @@ extern "C" size_t irlb200_slab_flow_work_bytes(int cnt) {
     return prog + sizeof(double) * (size_t)(cnt > 0 ? cnt : 0) + 256;
 }
 
+// peer-mapped block of a rank for irlb200_slab_flow (also valid for irlb200_slab_persistent):
+// [header | iterate 0 | iterate 1 | LL mailboxes for one ghost row from each neighbour, double-buffered]
+extern "C" size_t irlb200_slab_flow_block_bytes(int S_total, int halo) {
+    return flow_mail_offset(S_total) + 4 * sizeof(LLSlot) * (size_t)(halo > 0 ? halo : 0);
+}
+
+// zero the header and the mailboxes (all ranks, before any rank launches)
+extern "C" int irlb200_slab_flow_reset(void *block, int S_total, int halo, void *stream) {
+    if (!block || S_total <= 0 || halo < 0) return fail(IRLB200_EINVAL, "slab_flow_reset: bad argument");
+    cudaError_t e = cudaMemsetAsync(block, 0, kSlabHeaderBytes, (cudaStream_t)stream);
+    if (e == cudaSuccess && halo > 0)
+        e = cudaMemsetAsync(static_cast<unsigned char *>(block) + flow_mail_offset(S_total), 0,
+                            4 * sizeof(LLSlot) * (size_t)halo, (cudaStream_t)stream);
+    return e == cudaSuccess ? IRLB200_OK : fail_cuda(e, "cudaMemsetAsync(slab flow header)");
+}
+
 extern "C" int irlb200_slab_flow(int op, int rank, int world, void *const *blocks, int S_total, int lo, int cnt,
                                  int halo, int A, int K, const int32_t *idx, const double *p, const double *c0,
                                  const double *c1, const double *policy_in, const uint8_t *terminal_mask,
@@ -347,11 +429,6 @@ extern "C" int irlb200_slab_flow(int op, int rank, int world, void *const *block
     cudaStream_t st = (cudaStream_t)stream;
     SlabPeers pe{};
     for (int r = 0; r < world; ++r) pe.shared[r] = reinterpret_cast<SlabShared *>(blocks[r]);
-    auto bufs = [&](int r, int which) {
-        return reinterpret_cast<double *>(static_cast<unsigned char *>(blocks[r]) + kSlabHeaderBytes) + (size_t)which * S_total;
-    };
-    if (rank > 0) { pe.lo_buf0 = bufs(rank - 1, 0); pe.lo_buf1 = bufs(rank - 1, 1); }
-    if (rank < world - 1) { pe.hi_buf0 = bufs(rank + 1, 0); pe.hi_buf1 = bufs(rank + 1, 1); }
     pe.rank = rank; pe.world = world; pe.lo = lo; pe.hi = lo + cnt; pe.halo = halo;
     pe.timeout_ns = (long long)((timeout_s > 0 ? timeout_s : 20.0) * 1e9);
     unsigned char *base = static_cast<unsigned char *>(blocks[rank]);
@@ -364,9 +441,21 @@ extern "C" int irlb200_slab_flow(int op, int rank, int world, void *const *block
 
     const bool fast = (A == 4 && K == 5), compact = (A == 4 && K == 4);
     const void *k = nullptr;
-    if (op == 3) k = fast ? (const void *)slab_flow_kernel<3, 4, 5> : compact ? (const void *)slab_flow_kernel<3, 4, 4> : (const void *)slab_flow_kernel<3, 0, 0>;
-    else if (op == 1) k = fast ? (const void *)slab_flow_kernel<kOpSoftVI, 4, 5> : compact ? (const void *)slab_flow_kernel<kOpSoftVI, 4, 4> : (const void *)slab_flow_kernel<kOpSoftVI, 0, 0>;
-    else k = fast ? (const void *)slab_flow_kernel<kOpVI, 4, 5> : compact ? (const void *)slab_flow_kernel<kOpVI, 4, 4> : (const void *)slab_flow_kernel<kOpVI, 0, 0>;
+    // forward pass: states per thread in flight (U) x CTAs per SM; IRLB200_FLOW_FWD = 14 | 24 | 42 | 23 (U, CTAs/SM)
+    const int fwd = flow_env_int("IRLB200_FLOW_FWD", 24);
+    if (op == 3) {
+        if (fast) k = fwd == 14 ? (const void *)slab_flow_kernel<3, 4, 5, 1, 4> : fwd == 42 ? (const void *)slab_flow_kernel<3, 4, 5, 4, 2>
+                    : fwd == 23 ? (const void *)slab_flow_kernel<3, 4, 5, 2, 3> : (const void *)slab_flow_kernel<3, 4, 5, 2, 4>;
+        else if (compact) k = fwd == 14 ? (const void *)slab_flow_kernel<3, 4, 4, 1, 4> : fwd == 42 ? (const void *)slab_flow_kernel<3, 4, 4, 4, 2>
+                    : fwd == 23 ? (const void *)slab_flow_kernel<3, 4, 4, 2, 3> : (const void *)slab_flow_kernel<3, 4, 4, 2, 4>;
+        else k = (const void *)slab_flow_kernel<3, 0, 0, 1, 4>;
+    } else if (op == 1) {
+        k = fast ? (const void *)slab_flow_kernel<kOpSoftVI, 4, 5, 1, 3> : compact ? (const void *)slab_flow_kernel<kOpSoftVI, 4, 4, 1, 3>
+                 : (const void *)slab_flow_kernel<kOpSoftVI, 0, 0, 1, 3>;
+    } else {
+        k = fast ? (const void *)slab_flow_kernel<kOpVI, 4, 5, 1, 3> : compact ? (const void *)slab_flow_kernel<kOpVI, 4, 4, 1, 3>
+                 : (const void *)slab_flow_kernel<kOpVI, 0, 0, 1, 3>;
+    }
 
     const int threads = 256;
     int dev = 0, sms = 0, per_sm = 0;

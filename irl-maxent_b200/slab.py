@@ -265,7 +265,7 @@ class PeerSlabGrid(SlabGrid):
         E = self.backend.E
         self.E, self.ct = E, ctypes
         self.timeout_s = float(timeout_s)
-        nbytes = E._lib.irlb200_slab_block_bytes(self.n_states)
+        nbytes = E._lib.irlb200_slab_flow_block_bytes(self.n_states, self.halo)
         own = ctypes.c_void_p()
         E._check(E._lib.irlb200_peer_alloc(nbytes, ctypes.byref(own)))
         self._own, self._nbytes = own, nbytes
@@ -304,7 +304,7 @@ class PeerSlabGrid(SlabGrid):
         torch.cuda.synchronize()
         if self.world > 1:
             self.dist.barrier(group=self.group)
-        E._check(E._lib.irlb200_slab_reset(self._own, E._stream()))
+        E._check(E._lib.irlb200_slab_flow_reset(self._own, self.n_states, self.halo, E._stream()))
         torch.cuda.synchronize()
         if self.world > 1:
             self.dist.barrier(group=self.group)
