@@ -39,6 +39,21 @@ SVF_BYTES_PER_STATE_SWEEP = 84      # 20 + 8 w, w = 8: SURVEY section 8(d), merg
 BWD_BYTES_PER_STATE_SWEEP = 216     # 64 + 19 w
 
 
+def ncu_constants():
+    """Figures read off ncu captures, kept in a tracked file next to the summaries they come from."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_constants.json")))
+    except Exception:
+        return {}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -52,7 +67,7 @@ def parse():
                     help="guard per fixed point (the reference has none); worlds that hit it are reported")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the C1/C2/C3 side measurements")
-    ap.add_argument("--cpu-budget", type=float, default=240.0, help="seconds for the whole reference arm")
+    ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds for the whole reference arm")
     return ap.parse_args()
 
 
@@ -135,12 +150,18 @@ class ClockSampler:
 # CPU arm: the reference's dense numpy arithmetic (oracle/dense_port.py)
 # ---------------------------------------------------------------------------
 
-def blas_threads():
+def blas_threads(set_to=None):
+    """BLAS threads numpy's dgemv really uses.  `set_to`: raise the pool to that many threads first --
+    torch.distributed.run exports OMP_NUM_THREADS=1 to every rank, which would silently make the CPU
+    arm single-threaded at N >= 2."""
     try:
-        from threadpoolctl import threadpool_info
-        return max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+        import threadpoolctl
+        if set_to:
+            threadpoolctl.threadpool_limits(limits=int(set_to), user_api="blas")
+        return max([i.get("num_threads", 1) for i in threadpoolctl.threadpool_info()
+                    if i.get("user_api") == "blas"] + [1])
     except Exception:
-        return os.cpu_count() or 1
+        return 1
 
 
 def cpu_full_body(w, b):
@@ -185,16 +206,22 @@ def cpu_c_openmp(w, n_worlds=None):
     return nw / dt, threads, nw, dt, float(n_svf.mean())
 
 
-def cpu_sampled_body(w, b, n_bw=64, n_fw=256):
-    """Bounded sample of the same body: the per-call dense slicing / copy of the reference
-    (maxent.py:98-102,143) timed in full, n_bw backward and n_fw forward sweeps timed, then
-    scaled to 2S backward sweeps and to the exact forward sweep count of this world (taken
-    from the sparse restatement, not timed)."""
+def cpu_sampled_body(w, b, frac):
+    """Bounded sample of world b's gradient-step body with the reference's dense arithmetic
+    (oracle/dense_port.py restates maxent.py line by line; these are the same statements with the loops
+    cut short): the per-call dense slicing / copy (maxent.py:98-102,143) in full, then the first
+    `frac` of the 2S backward sweeps and the first `frac` of this world's forward sweeps.  The world's
+    exact forward sweep count comes from the sparse restatement (not timed).
+    Returns (measured seconds, seconds extrapolated to the whole body, detail)."""
     from oracle import dense_port as D
     from oracle import sparse_port as SP
     S, A = w["S"], 4
     P = D.icy_gridworld_table(w["n"], w["p_slip"][b])
     r = w["theta0"][b]
+    mdp = SP.icy_gridworld_sparse(w["n"], w["p_slip"][b])
+    pa = SP.local_action_probabilities(mdp, w["terminal"], r)
+    _, n_svf = SP.expected_svf_from_policy(mdp, w["p0"], w["terminal"], pa, 1e-5)
+    n_bw, n_fw = max(1, int(round(frac * 2 * S))), max(1, int(round(frac * n_svf)))
     t0 = time.perf_counter()
     er = np.exp(r)
     per_action = [np.array(P[:, :, a]) for a in range(A)]              # maxent.py:143
@@ -205,57 +232,70 @@ def cpu_sampled_body(w, b, n_bw=64, n_fw=256):
     for _ in range(n_bw):
         za = np.array([er * per_action[a].dot(zs) for a in range(A)]).T    # :155
         zs = za.sum(axis=1)                                                # :156
-    t_bw = (time.perf_counter() - t0) / n_bw
+    t_bw = time.perf_counter() - t0
     t0 = time.perf_counter()
     pt = np.copy(P)                                                    # :98
     pt[w["terminal"], :, :] = 0.0
     per_action_t = [np.array(pt[:, :, a]) for a in range(A)]           # :102
     t_setup_f = time.perf_counter() - t0
-    pol = np.full((S, A), 0.25)
     d = np.zeros(S)
     t0 = time.perf_counter()
     for _ in range(n_fw):
-        parts = [per_action_t[a].T.dot(pol[:, a] * d) for a in range(A)]   # :109
+        parts = [per_action_t[a].T.dot(pa[:, a] * d) for a in range(A)]    # :109
         d_new = w["p0"] + np.array(parts).sum(axis=0)                      # :110
         _delta, d = np.max(np.abs(d_new - d)), d_new                       # :112
-    t_fw = (time.perf_counter() - t0) / n_fw
-    mdp = SP.icy_gridworld_sparse(w["n"], w["p_slip"][b])
-    pa = SP.local_action_probabilities(mdp, w["terminal"], r)
-    _, n_svf = SP.expected_svf_from_policy(mdp, w["p0"], w["terminal"], pa, 1e-5)
-    total = t_setup_b + t_setup_f + 2 * S * t_bw + n_svf * t_fw
-    return total, n_svf, dict(setup_s=t_setup_b + t_setup_f, backward_ms_per_sweep=1e3 * t_bw,
-                              forward_ms_per_sweep=1e3 * t_fw)
+    t_fw = time.perf_counter() - t0
+    measured = t_setup_b + t_bw + t_setup_f + t_fw
+    whole = t_setup_b + t_setup_f + t_bw * (2.0 * S / n_bw) + t_fw * (float(n_svf) / n_fw)
+    return measured, whole, dict(setup_s=t_setup_b + t_setup_f, backward_sweeps_timed=n_bw, forward_sweeps_timed=n_fw,
+                                 forward_sweeps_of_the_world=int(n_svf),
+                                 backward_ms_per_sweep=1e3 * t_bw / n_bw, forward_ms_per_sweep=1e3 * t_fw / n_fw)
 
 
 def run_reference_arm(args):
+    """The reference's own CPU arithmetic for the same metric / config on the host cores.  Each step is a
+    bounded sample of one world's gradient-step body (see cpu_sampled_body): `ms_per_step` is what was
+    really timed, `value` = 1 / (that sample extrapolated to the whole body); one complete body is timed
+    beside it so that the extrapolation can be checked."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     w = workload(args, 0)
-    cores = blas_threads()
+    cores = blas_threads(set_to=os.cpu_count() or 1)
     total_steps = args.steps + args.warmup
-    full = total_steps * 40.0 <= args.cpu_budget and args.size <= 32
-    times, detail = [], None
+    # ~60 % of the budget for the timed samples, the rest for the sparse sweep counts and one full body
+    per_step = 0.6 * args.cpu_budget / max(1, total_steps)
+    frac = float(min(1.0, max(0.02, per_step / 16.0)))       # a whole 32 x 32 body takes ~12-18 s on 16-32 cores
+    measured, whole, detail = [], [], None
     for i in range(total_steps):
         b = (i * 409) % w["B"]
-        if full:
-            dt, n_svf = cpu_full_body(w, b)
-        else:
-            dt, n_svf, detail = cpu_sampled_body(w, b)
+        m, e, detail = cpu_sampled_body(w, b, frac)
+        if i == 0 and args.warmup > 0:                       # size the samples from the first (untimed) one
+            frac = float(min(1.0, max(0.02, frac * per_step / max(m, 1e-3))))
         if i >= args.warmup:
-            times.append(dt)
-    mean = float(np.mean(times))
-    value = 1.0 / mean
-    sample = ("one world of the batch per step, " +
-              ("full gradient-step body (2S dense backward sweeps + dense SVF sweeps to eps)" if full else
-               "per-call dense slicing timed in full + 64 backward + 256 forward dense sweeps timed, scaled to "
-               "2S backward sweeps and the world's exact forward sweep count (extrapolated)"))
+            measured.append(m)
+            whole.append(e)
+    mean_whole = float(np.mean(whole))
+    value = 1.0 / mean_whole
+    full_check = None
+    try:
+        b = (args.warmup * 409) % w["B"]                     # the first timed step's world, complete
+        t_full, n_svf = cpu_full_body(w, b)
+        full_check = {"world": int(b), "seconds": t_full, "extrapolated_seconds_same_world": whole[0],
+                      "forward_sweeps": int(n_svf)}
+    except Exception as e:                                   # pragma: no cover
+        full_check = {"error": repr(e)}
+    sample = ("one world of the batch per step: per-call dense slicing in full + the first %.0f %% of the 2S backward "
+              "and of the world's forward dense sweeps timed (ms_per_step), value = 1 / (sample extrapolated to the "
+              "whole body by the exact sweep counts); one complete body timed beside it (full_body_check)" % (100 * frac))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * mean, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(measured)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(args, args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                             "detail": detail},
+                             "sample_fraction": frac, "extrapolated_body_seconds": mean_whole, "detail": detail,
+                             "full_body_check": full_check,
+                             "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"), "host_cpus": os.cpu_count()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
@@ -418,11 +458,8 @@ def stream_roofline(n=2048, fw_sweeps=400, lap_sweeps=150):
     r = torch.full((S,), -0.1, dtype=torch.float64, device=dev); r[S - 1] = 1.0
     mask = torch.zeros(S, dtype=torch.uint8, device=dev); mask[S - 1] = 1
     phi = torch.full((S,), -float("inf"), dtype=torch.float64, device=dev); phi[S - 1] = 0.0
-    peak = 6650.0
-    try:
-        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-    except Exception:
-        pass
+    peak = float(measured_peaks().get("hbm_gbs", 6650.0))
+    ncu = ncu_constants()
     res = {"workload": "single %dx%d IcyGridWorld, streamed cooperative-grid kernels, fixed sweep budgets, "
                        "compact 4-slot tables" % (n, n),
            "states": S, "table_bytes": tabs.nbytes(), "peak": peak, "unit": "GB/s"}
@@ -446,12 +483,14 @@ def stream_roofline(n=2048, fw_sweeps=400, lap_sweeps=150):
         ach = bps * S * sweeps / (ms[name] / 1e3) / 1e9
         phys = moved[key] * S * sweeps / (ms[name] / 1e3) / 1e9
         res[key] = {"sweeps": sweeps, "launch_ms": ms[name], "us_per_sweep": 1e3 * ms[name] / sweeps,
-                    "bytes_per_state_sweep": bps, "achieved": ach, "frac": ach / peak,
-                    "moved_bytes_per_state_sweep": moved[key], "moved_GBps": phys, "moved_frac": phys / peak}
-    # ncu --set full of the forward launch with 5-slot tables (100 sweeps, profiles/r01_svf_streamed_2048x2048.txt):
-    # dram__bytes_read 32.80 GB + dram__bytes_write 3.56 GB = 364 MB per sweep against 352 MB moved by design
-    # ... and with the 4-slot tables (profiles/r01_svf_streamed_2048x2048_4slot.txt): 27.62 + 3.52 GB over 100 sweeps
-    res["forward"]["traffic_per_sweep"] = 311.4e6 if n == 2048 else None
+                    "bound": "hbm", "moved_bytes_per_state_sweep": moved[key], "achieved": phys, "frac": phys / peak,
+                    "survey_bytes_per_state_sweep": bps, "survey_equivalent_GBps": ach,
+                    "note": "achieved / frac count the bytes the kernel really moves with %d-slot tables; the SURVEY 8(d) "
+                            "figure assumes 5-slot tables and is kept as an equivalent only" % K}
+    # physical DRAM traffic of the same launches from ncu --set full captures (profiles/ncu_constants.json)
+    c4 = ncu.get("svf_streamed_2048x2048_4slot", {})
+    res["forward"]["traffic_per_sweep"] = c4.get("dram_bytes_per_sweep") if n == 2048 else None
+    res["forward"]["traffic_source"] = c4.get("source")
     res["forward"]["moved_bytes_per_sweep"] = float(moved["forward"]) * S
     res["forward"]["algorithmic_bytes_per_sweep"] = float(SVF_BYTES_PER_STATE_SWEEP) * S
     del tabs
@@ -459,8 +498,112 @@ def stream_roofline(n=2048, fw_sweeps=400, lap_sweeps=150):
     ms5 = timed(E.gridworld_tables(n, 0.2, slots=5))
     res["five_slot_tables"] = {"forward_us_per_sweep": 1e3 * ms5["svf"] / fw_sweeps,
                                "soft_vi_us_per_sweep": 1e3 * ms5["soft_vi"] / lap_sweeps,
-                               "forward_traffic_per_sweep_ncu": 363.6e6 if n == 2048 else None}
+                               "forward_traffic_per_sweep_ncu":
+                                   ncu.get("svf_streamed_2048x2048_5slot", {}).get("dram_bytes_per_sweep") if n == 2048 else None}
     return res
+
+
+def c5_slab(world, rank, dev, n=2048, fw_budget=10000, parity_n=256):
+    """BASELINE configs[4] under torchrun: ONE 2048x2048 IcyGridWorld (4.2 M states) sharded by state-row slabs
+    over the ranks (slab.PeerSlabGrid: one persistent dataflow kernel per GPU and fixed point, boundary rows
+    through NVLink mailboxes, no collective on the sweep path).  Causal soft-VI gamma = 0.9 to convergence and the
+    forward pass for a fixed sweep budget (convergence at this size needs 10^7+ sweeps), kernel
+    time from CUDA events on each rank, max over ranks.  Beside it: the barrier-per-sweep kernel of round 1, the
+    NCCL send/recv baseline, and a parity flag -- the N-rank result on a 256x256 world must be BITWISE the
+    1-GPU cooperative-grid kernel's (soft-VI policy and sweep count, forward SVF)."""
+    import torch
+    import torch.distributed as dist
+    import _irlb200 as E
+    import slab
+    S = n * n
+    peak = float(measured_peaks().get("hbm_gbs", 6650.0))
+    ref1 = ncu_constants().get("c5_single_gpu_reference", {})
+    out = {"workload": "single %dx%d IcyGridWorld, state-row slabs over %d GPUs, soft-VI gamma=0.9 eps=1e-5 to convergence + "
+                       "forward pass for %d sweeps (uniform policy: the diffuse worst case)" % (n, n, world, fw_budget),
+           "states": S, "states_per_gpu": S // world, "table_slots": 4}
+
+    def run(g, lap_budget, fw_b, reps):
+        r = np.full(g.cnt, -0.1); phi = np.full(g.cnt, -np.inf); p0 = np.zeros(g.cnt)
+        if g.hi == S:
+            r[-1] = 1.0; phi[-1] = 0.0
+        if g.lo == 0:
+            p0[0] = 1.0
+        uniform = torch.full((g.cnt, 4), 0.25, dtype=torch.float64, device=dev)
+        best = None
+        for _ in range(reps):
+            E.launch_log = []
+            torch.cuda.synchronize(); dist.barrier(); w0 = time.perf_counter()
+            g.soft_vi(r, phi, 0.9, 1e-5, max_sweeps=lap_budget)
+            n_lap = g.last_n_iter
+            torch.cuda.synchronize(); dist.barrier(); w1 = time.perf_counter()
+            d = g.svf(p0, [S - 1], uniform, 1e-5, max_sweeps=fw_b)
+            n_fw = g.last_n_iter
+            torch.cuda.synchronize(); dist.barrier(); w2 = time.perf_counter()
+            log, E.launch_log = E.launch_log, None
+            k = [a.elapsed_time(b) / 1e3 for nm, a, b in log if nm == "slab_persistent"]
+            t = torch.tensor(k[:2] if len(k) >= 2 else [w1 - w0, w2 - w1], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t = t.tolist()
+            if best is None or t[0] + t[1] < best[0] + best[1]:
+                best = (t[0], t[1], n_lap, n_fw, float(d.sum()))
+        return best
+
+    def describe(t_lap, t_fw, n_lap, n_fw, mass):
+        K = 4
+        moved_fw, moved_lap = 12 * K + 24, 4 * K + 32 * K + 24      # bytes per state and sweep with 4-slot tables
+        res = {"soft_vi_sweeps": n_lap, "soft_vi_us_per_sweep": 1e6 * t_lap / n_lap,
+               "forward_sweeps": n_fw, "forward_us_per_sweep": 1e6 * t_fw / n_fw,
+               "soft_vi_moved_GBps_aggregate": moved_lap * S * n_lap / t_lap / 1e9,
+               "forward_moved_GBps_aggregate": moved_fw * S * n_fw / t_fw / 1e9,
+               "forward_mass_local_rank0": mass}
+        res["soft_vi_frac_of_N_x_hbm_peak"] = res["soft_vi_moved_GBps_aggregate"] / (world * peak)
+        res["forward_frac_of_N_x_hbm_peak"] = res["forward_moved_GBps_aggregate"] / (world * peak)
+        if ref1:
+            res["soft_vi_strong_scaling_efficiency"] = ref1["soft_vi_us_per_sweep"] / (world * res["soft_vi_us_per_sweep"])
+            res["forward_strong_scaling_efficiency"] = ref1["forward_us_per_sweep"] / (world * res["forward_us_per_sweep"])
+        return res
+
+    g = slab.PeerSlabGrid(n, 0.2, flow=True)
+    out["dataflow_kernel"] = describe(*run(g, None, fw_budget, 2))
+    out["dataflow_kernel"]["note"] = ("csrc/slab_flow.cu; per-GPU working set %.0f MB (forward) / %.0f MB (soft-VI): at 8 GPUs it is "
+                                      "L2-resident, so the fraction of N x HBM peak is an equivalent there, not DRAM traffic"
+                                      % (72.0 * S / world / 1e6, 168.0 * S / world / 1e6))
+    g.close()
+    g = slab.PeerSlabGrid(n, 0.2, flow=False)
+    out["barrier_per_sweep_kernel_r01"] = describe(*run(g, 600, 1000, 2))
+    g.close()
+    g = slab.SlabGrid(n, 0.2, chunk=50)
+    t_lap, t_fw, n_lap, n_fw, _ = run(g, 100, 200, 2)
+    out["nccl_baseline"] = {"soft_vi_us_per_sweep": 1e6 * t_lap / n_lap, "forward_us_per_sweep": 1e6 * t_fw / n_fw,
+                            "note": "one launch + NCCL send/recv of the ghost rows per sweep, votes all-reduced per 50 sweeps; wall time"}
+    out["single_gpu_reference"] = ref1
+
+    # ---- parity: N ranks == the 1-GPU kernel, bitwise ------------------------------------------
+    m = parity_n
+    Sm = m * m
+    g = slab.PeerSlabGrid(m, 0.2, flow=True)
+    rng = np.random.default_rng(11)
+    rf = -0.1 + 0.02 * rng.standard_normal(Sm); rf[Sm - 1] = 1.0
+    phif = np.full(Sm, -np.inf); phif[Sm - 1] = 0.0
+    p0f = np.zeros(Sm); p0f[0] = 0.6; p0f[Sm // 2 + 3] = 0.4
+    pol, _ = g.soft_vi(g.local(rf), g.local(phif), 0.9, 1e-5)
+    n_lap = g.last_n_iter
+    d = g.svf(g.local(p0f), [Sm - 1], pol, 1e-5, max_sweeps=3000)
+    n_fw = g.last_n_iter
+    t1 = E.gridworld_tables(m, 0.2, slots=4)
+    pol1 = E.soft_vi(t1, E.terminal_phi([Sm - 1], Sm), rf, 0.9, mode=E.MODE_GRID)
+    n_lap1 = int(E.last_info.n_iter.item())
+    d1 = E.svf(t1, p0f, E.terminal_mask([Sm - 1], Sm), pol1, 1e-5, max_sweeps=3000, mode=E.MODE_GRID)
+    n_fw1 = int(E.last_info.n_iter.item())
+    ok = torch.tensor([int(bool((pol == pol1[0, g.lo:g.hi]).all()) and bool((d == d1[0, g.lo:g.hi]).all())
+                           and n_lap == n_lap1 and n_fw == n_fw1)], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    out["parity"] = {"world": "%dx%d over %d ranks vs the 1-GPU cooperative-grid kernel" % (m, m, world),
+                     "bitwise_equal_policy_and_svf_on_every_rank": bool(ok.item()),
+                     "soft_vi_sweeps": [n_lap, n_lap1], "forward_sweeps": [n_fw, n_fw1],
+                     "oracle_parity": "tests/test_gpu_multi.py (-m gpu, >= 2 devices): same run against oracle/c to 1e-10"}
+    g.close()
+    return out
 
 
 # ---------------------------------------------------------------------------
@@ -527,7 +670,8 @@ def run_b200_arm(args):
     launches = E.n_launches - l0
     log, E.launch_log = E.launch_log, None
     clocks = sampler.stop() if rank == 0 else None
-    ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    ms_rank = t0.elapsed_time(t1)
+    ms = torch.tensor([ms_rank], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
@@ -542,49 +686,47 @@ def run_b200_arm(args):
     bwd_ms = float(np.mean(dur.get("backward", [float("nan")])))
     svf_bytes = float(n_fw.mean()) * S * SVF_BYTES_PER_STATE_SWEEP
     bwd_bytes = float(B) * 2 * S * S * BWD_BYTES_PER_STATE_SWEEP
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = svf_bytes / (svf_ms / 1e3) / 1e9
-    # physical DRAM traffic of the same kernel: ncu --set full capture of this command line with
-    # --batch 444 (profiles/r01_svf_grid5_kernel.txt): 103.7 MB read + 5.5 MB written per launch of 444
-    # worlds = 246 kB per world (tables + policy in, svf/grad out, once per fixed point), scaled to B worlds
-    traffic = 246.0e3 * B if S == 1024 else None
-    roofline = {"bound": "hbm", "kernel": "svf_grid5_kernel (forward state-visitation sweeps, stencil-tiled)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
+    peaks = measured_peaks()
+    ncu = ncu_constants().get("svf_grid5_kernel", {})
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_equiv = svf_bytes / (svf_ms / 1e3) / 1e9
+    # The dominant kernel keeps tables, weights and the iterate on chip for the 10^4-10^5 sweeps of a launch, so
+    # HBM is not what bounds it (ncu: DRAM busy 0.2 %).  Its roofline is the shared-memory datapath: one
+    # wavefront of 128 B per clock per SM (scripts/ubench.cu, scripts/ubench_shfl.cu); a 2x4-tile thread moves
+    # 12 halo loads + 8 stores of 8 B per sweep = 160 wavefronts per 1024-state world-sweep (0 bank conflicts).
+    props = torch.cuda.get_device_properties(local)
+    n_sm = props.multi_processor_count
+    sm_clock_hz = 1e6 * float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0)
+    wf_per_ws = float(ncu.get("smem_wavefronts_per_1024_state_world_sweep", 160.0)) * S / 1024.0
+    smem_bytes = float(n_fw.mean()) * wf_per_ws * 128.0                   # per launch
+    smem_achieved = smem_bytes / (svf_ms / 1e3) / 1e9
+    smem_peak = 128.0 * n_sm * sm_clock_hz / 1e9
+    cyc = (svf_ms / 1e3) * sm_clock_hz * n_sm / float(n_fw.mean())
+    traffic = float(ncu["dram_bytes_per_world"]) * B if (S == 1024 and "dram_bytes_per_world" in ncu) else None
+    roofline = {"bound": "smem",
+                "kernel": "svf_grid5_kernel (forward state-visitation sweeps, stencil-tiled, one CTA per world)",
+                "achieved": smem_achieved, "peak": smem_peak, "unit": "GB/s", "frac": smem_achieved / smem_peak,
+                "peak_source": "128 B per clock per SM x %d SMs x the SM clock sampled during the timed region "
+                               "(%.0f MHz); shared-memory datapath width measured by scripts/ubench.cu" % (
+                                   n_sm, sm_clock_hz / 1e6),
+                "achieved_source": "shared-memory wavefronts per launch (%.0f per world-sweep x the launch's world-sweeps, "
+                                   "all counted live) x 128 B / CUDA-event time of the launch" % wf_per_ws,
                 "traffic": traffic,
-                "binding_resource": "on-chip: shared-memory datapath (ncu 80.6% of peak wavefronts at 3 worlds/SM), "
-                                    "FP64 pipe 51%, issue slots 42%; DRAM 0.2% busy (profiles/r01_svf_grid5_kernel.txt)",
-                "algorithmic_bytes_per_launch": svf_bytes, "launch_ms": svf_ms,
-                "share_of_step": svf_ms * args.steps / ms_total if ms_total else None,
+                "traffic_source": ncu.get("source"),
+                "sm_cycles_per_world_sweep": cyc, "smem_wavefronts_per_world_sweep": wf_per_ws,
+                "fp64_pipe_frac": float(ncu.get("fp64_pipe_cycles_per_1024_state_world_sweep", 110.0)) * S / 1024.0 / cyc,
+                "launch_ms": svf_ms, "share_of_step": svf_ms * args.steps / ms_total if ms_total else None,
                 "forward_sweeps_per_world_mean": float(n_fw.mean()) / B,
                 "forward_sweeps_per_world_max": int(max(int(s[:, 1].max().item()) for s in sweeps)),
                 "worlds_stopped_by_guard": int(sum(int((s[:, 1] == 2).sum().item()) for s in stati)),
-                "note": "tables, weights and the iterate are register/shared-memory resident for the whole fixed point "
-                        "(10^4-10^5 sweeps per launch), so the algorithmic bytes of a sweep never reach HBM: frac > 1 is "
-                        "an efficiency figure against the roofline a streaming implementation would hit, `traffic` is the "
-                        "physical DRAM volume; the physically HBM-bound regime is other_configs.roofline_stream "
-                        "(see DESIGN.md section 4)",
-                "backward": {"launch_ms": bwd_ms, "algorithmic_bytes_per_launch": bwd_bytes,
-                             "achieved": bwd_bytes / (bwd_ms / 1e3) / 1e9 if bwd_ms == bwd_ms else None}}
-
-    # the physical roofline of this kernel is on chip: 160 shared-memory wavefronts per 1024-state
-    # world-sweep (2x4 tiles: 12 halo loads + 8 stores of 8 B per thread, 128 B per wavefront, one
-    # wavefront per clock per SM -- scripts/ubench.cu, scripts/ubench_shfl.cu), measured live here
-    try:
-        props = torch.cuda.get_device_properties(local)
-        sm_clock_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
-        cyc = (svf_ms / 1e3) * sm_clock_hz * props.multi_processor_count / float(n_fw.mean())
-        roofline["onchip"] = {"resource": "shared-memory datapath (1 wavefront of 128 B per clock per SM)",
-                              "wavefronts_per_world_sweep": 160.0 * S / 1024.0,
-                              "sm_cycles_per_world_sweep": cyc, "frac": 160.0 * S / 1024.0 / cyc,
-                              "fp64_pipe_cycles_per_world_sweep": 110.0 * S / 1024.0}
-    except Exception:
-        pass
+                "launch_order": "longest-first by the previous step's sweep counts (IRLB200_LPT=%s)" % os.environ.get("IRLB200_LPT", "1"),
+                "hbm_equivalent": {
+                    "note": "NOT a roofline fraction: the algorithmic bytes of SURVEY 8(d) (84 B per state and sweep) that a "
+                            "streaming implementation would move, divided by the launch time, against the measured HBM copy "
+                            "bandwidth; the physically HBM-bound regime is other_configs.roofline_stream / c5_slab",
+                    "algorithmic_bytes_per_launch": svf_bytes, "GBps": hbm_equiv, "hbm_peak_GBps": hbm_peak,
+                    "ratio_to_hbm_peak": hbm_equiv / hbm_peak},
+                "backward": {"launch_ms": bwd_ms, "algorithmic_bytes_per_launch": bwd_bytes}}
 
     # ---- end to end through the public API with host buffers --------------------
     theta_h = torch.empty((B, S), dtype=torch.float64).pin_memory()
@@ -615,6 +757,34 @@ def run_b200_arm(args):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / (float(e2e_ms.item()) / 1e3)
 
+    # ---- per-rank breakdown: why weak scaling is not exactly 1.0 ---------------------------
+    # (no collective on the data path: a rank's time is its own work; `value` divides by the slowest rank)
+    mine = torch.tensor([ms_rank / args.steps, svf_ms, bwd_ms, float(n_fw.mean()),
+                         float(max(int(s[:, 1].max().item()) for s in sweeps))], dtype=torch.float64, device=dev)
+    allr = [torch.zeros_like(mine) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allr, mine)
+    else:
+        allr = [mine]
+    per_rank = [{"rank": r, "ms_per_step": float(t[0]), "forward_launch_ms": float(t[1]), "backward_launch_ms": float(t[2]),
+                 "forward_world_sweeps_per_step": float(t[3]), "forward_sweeps_max_world": int(t[4]),
+                 "ns_per_world_sweep": 1e6 * float(t[1]) / float(t[3])} for r, t in enumerate(allr)]
+    tot = np.array([r["forward_world_sweeps_per_step"] for r in per_rank])
+    tms = np.array([r["ms_per_step"] for r in per_rank])
+    rank_balance = {"work_max_over_mean": float(tot.max() / tot.mean()), "ms_max_over_mean": float(tms.max() / tms.mean()),
+                    "ms_max_over_rank0": float(tms.max() / tms[0]),
+                    "note": "every rank draws its own 4096 rewards (weak scaling), so the ranks' total forward sweeps differ; "
+                            "the driver's efficiency v_N / (N v_1) compares the slowest rank with rank 0's own batch"}
+
+    c5 = None
+    if world > 1 and not args.no_other_configs:
+        del tabs, e_features, theta
+        torch.cuda.empty_cache()
+        try:
+            c5 = c5_slab(world, rank, dev)
+        except Exception as e:                                             # side measurements never sink the line
+            c5 = {"error": repr(e)}
+
     line = None
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -623,7 +793,10 @@ def run_b200_arm(args):
                 "config": config_dict(args, world), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * S * 8,
                         "d2h_bytes_per_step": B * S * 8},
-                "gpu_launches": int(launches), "roofline": roofline}
+                "gpu_launches": int(launches), "roofline": roofline,
+                "per_rank": per_rank, "rank_balance": rank_balance}
+        if c5 is not None:
+            line["other_configs"] = {"C5_slab": c5}
         if world == 1 and not args.no_other_configs:
             try:
                 line["other_configs"] = other_configs()

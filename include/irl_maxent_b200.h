@@ -12,6 +12,11 @@
  *   - Every pointer is a DEVICE pointer unless its name starts with `h_`.
  *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  All
  *     work is enqueued on it; nothing synchronises the host unless documented.
+ *     Internal scratch (barrier words and iterate buffers of the cooperative-grid
+ *     mode, weight scratch of the streamed forward pass) is cached per
+ *     (device, stream): calls on different streams never share it, calls on one
+ *     stream are ordered by the stream.  Entry points that take a caller-owned
+ *     work buffer (irlb200_slab_flow) use no internal scratch at all.
  *   - Every function returns 0 on success, a negative IRLB200_E* code otherwise;
  *     irlb200_last_error() gives a message for the calling thread.
  *   - Values are IEEE float64 (the reference computes in float64 only);

@@ -275,22 +275,46 @@ def gridworld_dense(size, p_slip=0.2, icy=True):
 # ---- cache: the reference API hands the dense table to every call ------------
 
 _cache = {}
+_FULL_HASH_BYTES = 64 << 20        # arrays up to this size are fingerprinted in full on every call
 
 
 def clear_cache():
+    """Forget every compressed table (see `as_tables`)."""
     _cache.clear()
+
+
+def invalidate(p_transition):
+    """Forget the tables compressed from this array / tensor (after editing a very large one in place)."""
+    _cache.pop(id(p_transition), None)
+
+
+def _fingerprint(p):
+    """Cheap content fingerprint of a dense table, so that an IN-PLACE edit between two calls is seen
+    (the reference re-reads the array on every call).  CUDA / CPU tensors: torch's version counter
+    (bumped by every in-place op) + storage address.  numpy arrays: crc32 of the whole buffer up to
+    64 MiB (33.5 MB = a 32x32 world: ~15 ms); beyond that crc32 of 4 M evenly strided elements plus the
+    corners -- an edit that misses all of them needs `invalidate(p)` / `clear_cache()`."""
+    import zlib
+    if is_tensor(p):
+        return ("t", p._version, p.data_ptr(), tuple(p.shape))
+    a = np.asarray(p)
+    if a.nbytes <= _FULL_HASH_BYTES:
+        return ("n", zlib.crc32(np.ascontiguousarray(a).view(np.uint8).reshape(-1)), a.shape)
+    flat = a.reshape(-1) if a.flags.c_contiguous else a.ravel()
+    step = max(1, flat.size // (4 << 20))
+    sample = np.ascontiguousarray(flat[::step])
+    return ("s", zlib.crc32(sample.view(np.uint8)), float(flat[0]), float(flat[-1]), a.shape)
 
 
 def as_tables(p_transition):
     """Tables for whatever the caller passed as `p_transition` (dense array, CUDA
     tensor or an existing handle).  Dense inputs are compressed once and cached by
-    object identity (small arrays additionally by content hash), because the
-    reference API passes the same dense table to every call of the inner loop."""
+    object identity + content fingerprint (`_fingerprint`), because the reference
+    API passes the same dense table to every call of the inner loop."""
     if isinstance(p_transition, Tables):
         return p_transition
     key = id(p_transition)
-    small = not is_tensor(p_transition) and getattr(p_transition, "nbytes", 1 << 62) <= (1 << 20)
-    digest = hash(np.ascontiguousarray(p_transition).tobytes()) if small else None
+    digest = _fingerprint(p_transition)
     hit = _cache.get(key)
     if hit is not None and hit[1] == digest and hit[2]() is p_transition:
         return hit[0]

@@ -1,7 +1,9 @@
 // host_util.cu -- error strings, device probing, workspace cache.
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <tuple>
 
 #include "host_util.h"
 
@@ -31,21 +33,23 @@ int device_count_impl() {
 namespace {
 constexpr int kSlots = 4, kMaxDev = 16;
 struct Slot { void *ptr = nullptr; size_t bytes = 0; };
-Slot g_ws[kMaxDev][kSlots];
+// one block per (device, slot, STREAM): calls issued on different streams (or from different host threads
+// on their own streams) never share barrier words, iterate buffers or weight scratch
+std::map<std::tuple<int, int, cudaStream_t>, Slot> g_ws;
 std::mutex g_mu;
 }  // namespace
 
-int workspace(int slot, size_t bytes, void **out) {
+int workspace(int slot, size_t bytes, void **out, cudaStream_t stream) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return fail_cuda(e, "cudaGetDevice");
     if (dev >= kMaxDev || slot >= kSlots) return fail(IRLB200_EINVAL, "workspace: bad slot/device");
     std::lock_guard<std::mutex> lk(g_mu);
-    Slot &s = g_ws[dev][slot];
+    Slot &s = g_ws[std::make_tuple(dev, slot, stream)];
     if (s.bytes < bytes) {
         if (s.ptr) {
-            // earlier launches may still read the old block: drain before freeing
-            cudaDeviceSynchronize();
+            // earlier launches on this stream may still use the old block: drain that stream only
+            cudaStreamSynchronize(stream);
             cudaFree(s.ptr);
             s.ptr = nullptr;
             s.bytes = 0;

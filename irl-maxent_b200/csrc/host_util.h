@@ -12,10 +12,10 @@ int fail(int code, const char *msg);
 int fail_cuda(cudaError_t e, const char *what);
 int device_count_impl();
 
-// Cached per-device scratch allocations, grown on demand and reused by later
-// calls (slot 0: predecessor weights of the streamed forward pass, slot 1:
-// iterate buffers + barrier state of the cooperative kernels, slot 2: misc).
-// Calls that use the same slot must be issued on one stream per device.
-int workspace(int slot, size_t bytes, void **out);
+// Cached scratch allocations, one block per (device, slot, stream), grown on demand and reused by later
+// calls on the same stream (slot 0: predecessor weights of the streamed forward pass, slot 1: iterate
+// buffers + barrier state of the cooperative kernels).  Launches on one stream are ordered, so reuse
+// within a stream is safe; different streams get different blocks.
+int workspace(int slot, size_t bytes, void **out, cudaStream_t stream);
 
 }  // namespace irlb200

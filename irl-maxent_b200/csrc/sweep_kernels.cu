@@ -324,7 +324,7 @@ static int launch_svf_cta(SvfBatch bt, int B, cudaStream_t st) {
     } else {
         if (A > kMaxDynA) return fail(IRLB200_EINVAL, "run-time A > 16 is not supported");
         double *ws = nullptr;
-        if (int rc = workspace(0, (size_t)B * S * K * sizeof(double), (void **)&ws)) return rc;
+        if (int rc = workspace(0, (size_t)B * S * K * sizeof(double), (void **)&ws, st)) return rc;
         bt.a.w_scratch = ws;
         if (fast) {
             auto k = svf_cta_kernel<4, 5, 0, 1024, 1>;
@@ -368,7 +368,7 @@ static int launch_step_cta(StepBatch bt, int B, cudaStream_t st) {
         if (A > kMaxDynA) return fail(IRLB200_EINVAL, "run-time A > 16 is not supported");
         if (bt.s.K != bt.f.K && fast) return fail(IRLB200_EINVAL, "internal: fused fast shape mismatch");
         double *ws = nullptr;
-        if (int rc = workspace(0, (size_t)B * S * bt.f.K * sizeof(double), (void **)&ws)) return rc;
+        if (int rc = workspace(0, (size_t)B * S * bt.f.K * sizeof(double), (void **)&ws, st)) return rc;
         bt.f.w_scratch = ws;
         if (fast) {
             auto k = step_cta_kernel<CAUSAL, 4, 5, 0, 1024>;
@@ -414,7 +414,7 @@ static int grid_work(int S, GridWork *w, cudaStream_t st) {
     // workspace slot 1: [GridSyncState | buf0 | buf1]
     const size_t hdr = 256;
     unsigned char *base = nullptr;
-    if (int rc = workspace(1, hdr + 2 * (size_t)S * sizeof(double), (void **)&base)) return rc;
+    if (int rc = workspace(1, hdr + 2 * (size_t)S * sizeof(double), (void **)&base, st)) return rc;
     w->gs = reinterpret_cast<GridSyncState *>(base);
     w->buf0 = reinterpret_cast<double *>(base + hdr);
     w->buf1 = w->buf0 + S;
@@ -503,7 +503,7 @@ static int launch_svf_grid(SvfArgs a, int32_t *n_iter, int32_t *status, cudaStre
         }
     }
     double *ws = nullptr;
-    if (int rc = workspace(0, (size_t)a.S * a.K * sizeof(double), (void **)&ws)) return rc;
+    if (int rc = workspace(0, (size_t)a.S * a.K * sizeof(double), (void **)&ws, st)) return rc;
     a.w_scratch = ws;
     if (fast) {
         auto k = svf_grid_kernel<4, 5, 0, 512, 1>;

@@ -285,7 +285,7 @@ extern "C" int irlb200_dense_fill(const double *P, int S, int A, int Ks, int Kp,
     if (device_count_impl() <= 0) return fail(IRLB200_ECUDA, "no CUDA device");
     cudaStream_t st = (cudaStream_t)stream;
     int32_t *cursor = nullptr;
-    if (int rc = workspace(2, sizeof(int32_t) * (size_t)S, (void **)&cursor)) return rc;
+    if (int rc = workspace(2, sizeof(int32_t) * (size_t)S, (void **)&cursor, st)) return rc;
     cudaMemsetAsync(cursor, 0, sizeof(int32_t) * S, st);
     dense_rows_kernel<true><<<S, 256, 0, st>>>(P, S, A, Ks, Kp, nullptr, nullptr, nullptr,
                                                succ_idx, succ_p, pred_idx, pred_p, cursor);

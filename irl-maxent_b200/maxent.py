@@ -13,7 +13,10 @@ Type rule: numpy in -> numpy out, CUDA tensor in -> CUDA tensor out.
 `p_transition` may be the reference's dense `[S, S', A]` table (numpy or CUDA
 tensor; compressed once and cached) or a pre-built `_irlb200.Tables` handle
 (e.g. `gridworld.IcyGridWorld(...).tables()`), which is the only option for
-state counts whose dense table cannot exist.
+state counts whose dense table cannot exist.  The cache notices in-place edits
+of the table between calls (content fingerprint: every byte up to 64 MiB, a
+4 M-element sample beyond; tensors by version counter); after editing a larger
+array in place call `maxent.invalidate(p_transition)` or `maxent.clear_cache()`.
 
 Differences from the reference, by design:
   * the non-causal backward pass is range-extended (exact power-of-two
@@ -28,6 +31,7 @@ Differences from the reference, by design:
 import numpy as np
 
 import _irlb200 as E
+from _irlb200 import clear_cache, invalidate      # noqa: F401  (table-cache control, see the module docstring)
 
 
 # -- helpers -------------------------------------------------------------------

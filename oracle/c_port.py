@@ -89,12 +89,16 @@ def soft_vi(sidx, sp, phi, reward, discount, eps=1e-5, max_sweeps=0):
     return pol, val, n.value
 
 
-def svf(sidx, sp, p0, terminal, policy, eps=1e-5, max_sweeps=0):
+def svf(sidx, sp, p0, terminal, policy, eps=1e-5, max_sweeps=0, threads=None):
+    """threads: None = the OpenMP gather form for S >= 4096 (bitwise the serial loop, see irl_oracle.c),
+    True / False force it."""
     S, A, K = sp.shape
     d, n = np.empty(S), ctypes.c_long(0)
     p0 = np.ascontiguousarray(p0, dtype=np.float64)
     policy = np.ascontiguousarray(policy, dtype=np.float64)
-    rc = load().oracle_svf(S, A, K, _p(sidx, ctypes.c_int), _p(sp, ctypes.c_double), _p(p0, ctypes.c_double),
+    mt = (S >= 4096) if threads is None else bool(threads)
+    fn = load().oracle_svf_mt if mt else load().oracle_svf
+    rc = fn(S, A, K, _p(sidx, ctypes.c_int), _p(sp, ctypes.c_double), _p(p0, ctypes.c_double),
                            _p(_mask(terminal, S), ctypes.c_ubyte), _p(policy, ctypes.c_double),
                            ctypes.c_double(eps), ctypes.c_long(max_sweeps), _p(d, ctypes.c_double), ctypes.byref(n))
     assert rc == 0

@@ -29,12 +29,43 @@ class _Inert(types.ModuleType):
         return _Inert("call")
 
 
+def _count_outer_steps():
+    """IRLB200_MAIN_REPORT=1: count the optimizer steps of every `irl` / `irl_causal` call (one per outer
+    gradient step, maxent.py:251 / :449) by wrapping the ENGINE's optimizer classes -- main.py itself stays
+    untouched -- and print them when the script ends."""
+    import atexit
+    import optimizer as O
+    runs = []
+
+    def wrap(cls):
+        reset, step = cls.reset, cls.step
+
+        def counted_reset(self, parameters):
+            runs.append(0)
+            return reset(self, parameters)
+
+        def counted_step(self, grad, *a, **k):
+            runs[-1] += 1
+            return step(self, grad, *a, **k)
+
+        cls.reset, cls.step = counted_reset, counted_step
+
+    for name in ("Sga", "ExpSga"):
+        wrap(getattr(O, name))
+    atexit.register(lambda: print("IRLB200_MAIN_OUTER_STEPS %s" % " ".join(str(n) for n in runs), flush=True))
+
+
 def main(path):
     try:
         import matplotlib  # noqa: F401
     except ImportError:
         sys.modules["matplotlib"] = _Inert("matplotlib")
         sys.modules["matplotlib.pyplot"] = _Inert("matplotlib.pyplot")
+    if os.environ.get("IRLB200_MAIN_SEED"):
+        import numpy as np
+        np.random.seed(int(os.environ["IRLB200_MAIN_SEED"]))     # main.py draws its expert data from np.random
+    if os.environ.get("IRLB200_MAIN_REPORT"):
+        _count_outer_steps()
     return runpy.run_path(path, run_name="__main__")
 
 

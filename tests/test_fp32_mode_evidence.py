@@ -1,4 +1,4 @@
-"""Why there is no fp32 mode (DESIGN.md section 2, "Deliberate differences").
+"""Why there is no fp32 mode (DESIGN.md section 2, "Deliberate differences"; BASELINE.md section 5).
 
 BASELINE.json's north star allows an fp32 mode "within 1e-5".  This measures, with the CPU oracle only,
 what the most favourable fp32 mode could reach: tables and policy STORED in fp32, every operation
@@ -40,3 +40,83 @@ def test_fp32_storage_holds_1e5_only_on_the_5x5_world():
     assert rel16 > 1e-5                                      # 1.95e-5 measured
     rel32, a32, b32 = _svf_pair(32)
     assert rel32 > 5e-5 and a32 != b32                       # 1.2e-4 measured; 19 948 vs 19 950 sweeps
+
+
+# ---------------------------------------------------------------------------------------------
+# The policy passes in an fp32 LOG-SPACE mode (what the north star sketches), emulated with numpy
+# float32 arithmetic over the oracle's tables.  Measured (max relative error against the fp64 oracle):
+#
+#   size   soft-VI policy   soft-VI sweeps fp64 / fp32   backward policy   forward SVF fed by the fp32 policy
+#   5x5    1.7e-6           770 / 240                    4.5e-7            3.3e-6   (753 / 753 sweeps)
+#   16x16  3.2e-6           868 / 276                    9.7e-7            2.2e-5   (14 822 / 14 822)
+#   32x32  2.7e-6           925 / 325                    6.9e-6            2.8e-4   (61 636 / 61 621)
+#   64x64  3.5e-6           1 023 / 412                  9.8e-6            2.7e-4   (152 131 / 152 119)
+#
+# So: the two POLICY passes would hold 1e-5 in fp32 log space up to 64x64 (the backward error grows with
+# the 2S chained sweeps and reaches the bar there), but (a) the soft-VI sweep count cannot be the
+# reference's -- it is set by the decay of the -1e200 start value (maxent.py:323), which fp32 cannot
+# hold -- and (b) the forward pass amplifies the policy's 1e-6 error by the mixing time, missing the 1e-5
+# bar on the SVF from 16x16 on even when every forward sweep is computed in fp64, and its sweep count
+# moves.  "fp32 within 1e-5 with identical iteration counts" is reachable on the 5x5 configs only
+# (C1 / C2: 25 states, where precision buys nothing); the decision not to build the mode is closed.
+# ---------------------------------------------------------------------------------------------
+
+def _soft_vi_np(sidx, sp, phi, r, gamma, eps, dt, init):
+    S = sp.shape[0]
+    sp, r, phi, gamma = sp.astype(dt), r.astype(dt), phi.astype(dt), dt(gamma)
+    v = np.full(S, init, dtype=dt)
+    n = 0
+    while True:
+        q = r[:, None] + gamma * (sp * v[sidx]).sum(axis=2, dtype=dt)
+        x = np.concatenate([phi[:, None], q], axis=1)
+        m = x.max(axis=1)
+        with np.errstate(over="ignore", invalid="ignore"):
+            vn = (m + np.log(np.exp(x - m[:, None]).sum(axis=1, dtype=dt))).astype(dt)
+        delta, v, n = np.max(np.abs(vn - v)), vn, n + 1
+        if not (delta > eps) or n > 100000:
+            return np.exp(q - v[:, None]), n
+
+
+def _backward_log_np(sidx, sp, terminal, r, dt):
+    S = sp.shape[0]
+    with np.errstate(divide="ignore"):
+        lp = np.log(sp).astype(dt)
+    r = r.astype(dt)
+    lz = np.full(S, -np.inf, dtype=dt)
+    lz[terminal] = 0
+
+    def lse(x, axis):
+        m = x.max(axis=axis)
+        safe = np.where(np.isfinite(m), m, 0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            out = safe + np.log(np.exp(x - np.expand_dims(safe, axis)).sum(axis=axis, dtype=dt))
+        return np.where(np.isfinite(m), out, -np.inf).astype(dt)
+
+    for _ in range(2 * S):
+        lza = lse(lp + lz[sidx], 2) + r[:, None]
+        lz = lse(lza, 1)
+    return np.exp(lza - lz[:, None])
+
+
+@pytest.mark.parametrize("n", [5, 16])
+def test_fp32_log_space_policy_passes_and_what_the_forward_pass_makes_of_them(n):
+    S = n * n
+    sidx, sp = C.ell_from_sparse(SP.icy_gridworld_sparse(n, 0.2))
+    r = np.full(S, -0.1); r[S - 1] = 1.0
+    phi = np.full(S, -np.inf); phi[S - 1] = 0.0
+    p64, _, n64 = C.soft_vi(sidx, sp, phi, r, 0.9, 1e-5)
+    e64, m64 = _soft_vi_np(sidx, sp, phi, r, 0.9, 1e-5, np.float64, -1e200)
+    assert m64 == n64 and np.max(np.abs(e64 - p64) / p64) < 1e-12          # the emulation is the oracle's loop
+    p32, n32 = _soft_vi_np(sidx, sp, phi, r, 0.9, 1e-5, np.float32, -3e38)
+    assert np.max(np.abs(p32 - p64) / p64) < 1e-5                          # the policy itself would pass ...
+    assert n32 < n64 // 2                                                  # ... the sweep count cannot
+    rm = -np.log(4.0) + 0.01 * np.random.default_rng(0).standard_normal(S)
+    b64 = C.backward(sidx, sp, [S - 1], rm, rescale=True)
+    assert np.max(np.abs(_backward_log_np(sidx, sp, [S - 1], rm, np.float64) - b64) / b64) < 1e-12
+    b32 = _backward_log_np(sidx, sp, [S - 1], rm, np.float32).astype(np.float64)
+    assert np.max(np.abs(b32 - b64) / b64) < 1e-5
+    p0 = np.zeros(S); p0[0] = 1.0
+    d64, _ = C.svf(sidx, sp, p0, [S - 1], b64)
+    d32, _ = C.svf(sidx, sp, p0, [S - 1], b32)
+    rel = float(np.max(np.abs(d32 - d64) / np.maximum(d64, 1e-300)))
+    assert (rel < 1e-5) if n == 5 else (rel > 1e-5)                        # 3.3e-6 at 5x5, 2.2e-5 at 16x16

@@ -274,6 +274,29 @@ def test_module_api_tensor_in_tensor_out(golden):
     close(v, g["k5_vi"])
 
 
+def test_in_place_edit_of_a_dense_table_is_not_served_from_the_cache():
+    """The reference re-reads p_transition on every call; the table cache must notice an in-place edit of a
+    table larger than 1 MiB (16x16: 2 MB) and of a CUDA tensor."""
+    n = 16
+    S = n * n
+    P = D.icy_gridworld_table(n, 0.2)
+    assert P.nbytes > (1 << 20)
+    r = -0.1 * np.ones(S); r[S - 1] = 1.0
+    import solver as SV
+    v0 = SV.value_iteration(P, r, 0.9, 1e-6)
+    P[:] = D.icy_gridworld_table(n, 0.35)                # same object, new contents
+    v1 = SV.value_iteration(P, r, 0.9, 1e-6)
+    ref, _ = D.value_iteration(P, r, 0.9, 1e-6)
+    close(v1, ref)
+    assert np.max(np.abs(v1 - v0)) > 1e-6
+    Pt = E.to_device(D.icy_gridworld_table(n, 0.2))
+    w0 = SV.value_iteration(Pt, E.to_device(r), 0.9, 1e-6)
+    close(w0, v0)
+    Pt.copy_(E.to_device(P))                             # in place on the device
+    w1 = SV.value_iteration(Pt, E.to_device(r), 0.9, 1e-6)
+    close(w1, ref)
+
+
 def test_fused_step_matches_split(golden):
     g = golden("kernels")
     t = E.gridworld_tables(8, 0.2)
@@ -344,6 +367,34 @@ def test_irl_causal_5x5_like_main(golden, gamma):
     r = M.irl_causal(world.p_transition, W.state_features(world), [24], tjs, opt, O.Constant(1.0), gamma)
     assert opt.n == int(g["irl_causal_%s_steps" % gamma])
     close(r, g["irl_causal_%s_reward" % gamma])
+
+
+def test_the_reference_main_py_runs_unchanged_on_the_gpu(golden):
+    """BASELINE north_star: `src/main.py` runs unchanged against the engine.  tests/golden/reference_main_py.fixture
+    is a byte-identical copy of the reference's driver (the one verbatim file in this repository: the CALLER that
+    must run unmodified; sha256 pinned here and checked against /root/reference/src/main.py where that exists,
+    MIT licence beside it).  It is launched through scripts/run_reference_main.py in a fresh interpreter with
+    np.random.seed(0); the engine's optimizer classes count the outer steps: 375 (irl) and 419 (irl_causal,
+    gamma = 0.7 as in main.py:75) -- the reference's own counts (SURVEY 8c, KAT5 / tests/golden/e2e_5x5.npz)."""
+    import hashlib
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fixture = os.path.join(root, "tests", "golden", "reference_main_py.fixture")
+    digest = hashlib.sha256(open(fixture, "rb").read()).hexdigest()
+    assert digest == "e0f6c933ba28e01809804ddef95d3bdab221edf6da25bc4e1b890b25dbca2cb1"
+    ref = "/root/reference/src/main.py"
+    if os.path.exists(ref):
+        assert hashlib.sha256(open(ref, "rb").read()).hexdigest() == digest
+    env = dict(os.environ, IRLB200_MAIN_SEED="0", IRLB200_MAIN_REPORT="1")
+    p = subprocess.run([sys.executable, os.path.join(root, "scripts", "run_reference_main.py"), fixture],
+                       capture_output=True, text=True, timeout=280, env=env)
+    assert p.returncode == 0, p.stderr[-3000:]
+    line = [ln for ln in p.stdout.splitlines() if ln.startswith("IRLB200_MAIN_OUTER_STEPS")]
+    assert line, p.stdout[-2000:]
+    steps = [int(v) for v in line[-1].split()[1:]]
+    g = golden("e2e_5x5")
+    assert steps == [int(g["irl_steps"]), int(g["irl_causal_0.7_steps"])] == [375, 419]
 
 
 def test_irl_other_optimizers_and_dense_features(golden):
@@ -723,8 +774,9 @@ def test_cluster_push_backward_equals_one_cta_tiled_kernel(n, size, regime, monk
 
 
 def test_cluster_push_backward_128(monkeypatch):
-    """128 x 128 (BASELINE configs[2]): AUTO takes the cluster kernel; policy == per-action cooperative-grid
-    sweeps to 1e-10 and == the sparse oracle's range-extended loop."""
+    """128 x 128 (BASELINE configs[2]): AUTO takes the cluster kernel; cluster policy == the per-action
+    cooperative-grid sweeps to 1e-10 (a cross-variant check; the comparison with the oracle's range-extended
+    loop at this size is test_c3_full_size_values_against_the_c_oracle)."""
     n = 128; S = n * n
     t = E.gridworld_tables(n, 0.2)
     r = -np.log(4.0) + 0.01 * np.random.default_rng(0).standard_normal(S)
@@ -942,6 +994,45 @@ def test_c3_full_size_counts_and_fixed_point():
     # d[terminal] is the probability mass absorbed so far; the reference's loose stop rule
     # (delta <= 1e-5) ends the loop with part of the mass still under way at this size
     assert 0.5 < dn[Sn - 1] <= 1.0
+
+
+@pytest.mark.timeout(900)
+def test_c3_full_size_values_against_the_c_oracle(monkeypatch):
+    """C3 at full size, VALUES against the plain-C oracle (oracle/c/irl_oracle.c) to 1e-10 with exact counts:
+    soft-VI policy (cooperative grid AND thread-block cluster), forward SVF of the causal and of the MaxEnt
+    body (cluster push kernel), and the cluster backward policy against the oracle's range-extended loop."""
+    from oracle import c_port as C
+    n = 128
+    S = n * n
+    t = E.gridworld_tables(n, 0.2)
+    sidx, sp = C.ell_from_sparse(SP.icy_gridworld_sparse(n, 0.2))
+    mask, phi_d = E.terminal_mask([S - 1], S), E.terminal_phi([S - 1], S)
+    phi = np.full(S, -np.inf); phi[S - 1] = 0.0
+    p0 = np.zeros(S); p0[0] = 1.0
+    # causal body: goal-directed reward
+    r = np.full(S, -0.1); r[S - 1] = 1.0
+    pol_c, _, n_c = C.soft_vi(sidx, sp, phi, r, 0.9, 1e-5)
+    for mode in (E.MODE_GRID, E.MODE_AUTO):
+        pol = E.soft_vi(t, phi_d, r, 0.9, mode=mode)
+        assert counts()[0] == n_c == 1208
+        close(pol[0], pol_c)
+    d_c, n_dc = C.svf(sidx, sp, p0, [S - 1], pol_c, 1e-5)
+    d = E.svf(t, p0, mask, pol, 1e-5)                            # AUTO -> cluster push kernel
+    assert counts()[0] == n_dc == 243869
+    close(d[0], d_c)
+    # MaxEnt body: reward near -ln 4 (the regime in which the raw reference is finite, SURVEY TL;DR 2)
+    rm = -np.log(4.0) + 0.01 * np.random.default_rng(0).standard_normal(S)
+    pb_c = C.backward(sidx, sp, [S - 1], rm, rescale=True)
+    pb = E.backward(t, mask, rm)                                 # AUTO -> cluster push kernel
+    close(pb[0], pb_c)
+    monkeypatch.setenv("IRLB200_BWD_TILE", "0")                  # per-action sweeps behind the grid barrier
+    pb_g = E.backward(t, mask, rm, mode=E.MODE_GRID)
+    close(pb_g[0], pb_c)
+    monkeypatch.delenv("IRLB200_BWD_TILE")
+    dm_c, n_mc = C.svf(sidx, sp, p0, [S - 1], pb_c, 1e-5)
+    dm = E.svf(t, p0, mask, pb, 1e-5)
+    assert counts()[0] == n_mc
+    close(dm[0], dm_c)
 
 
 def test_c4_sampled_worlds_of_the_full_batch():

@@ -304,3 +304,30 @@ def test_terminal_must_be_indices_for_the_forward_pass():
         E.terminal_mask(np.full(9, -1.5), 9)
     with pytest.raises(E.EngineError, match="state indices"):
         E.terminal_mask([3, 9], 9)
+
+
+def test_table_cache_fingerprint_sees_in_place_edits():
+    """the dense-table cache must not hand out stale tables after an in-place edit.  The
+    fingerprint covers every byte up to 64 MiB (also > 1 MiB, the old limit), a strided sample beyond,
+    and torch tensors through their version counter."""
+    import torch
+    small = np.zeros((25, 25, 4)); small[0, 1, 2] = 0.5
+    f0 = E._fingerprint(small)
+    assert E._fingerprint(small) == f0
+    small[3, 4, 1] = 0.25
+    assert E._fingerprint(small) != f0
+    mid = np.zeros((300, 300, 4))                       # 2.9 MB: was identity-only in round 1
+    f0 = E._fingerprint(mid)
+    mid[299, 17, 3] = 1e-9
+    assert E._fingerprint(mid) != f0
+    big = np.zeros((1500, 1500, 4))                     # 72 MB: sampled
+    f0 = E._fingerprint(big)
+    assert f0[0] == "s" and E._fingerprint(big) == f0
+    big[:] = 0.125
+    assert E._fingerprint(big) != f0
+    t = torch.zeros(8, 8, 4, dtype=torch.float64)
+    f0 = E._fingerprint(t)
+    t[1, 2, 3] = 1.0
+    assert E._fingerprint(t) != f0
+    import maxent as M
+    assert M.invalidate is E.invalidate and M.clear_cache is E.clear_cache

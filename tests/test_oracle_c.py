@@ -67,3 +67,23 @@ def test_c_oracle_batch_and_sparse_tables(golden):
     ref, n_ref = D.compute_expected_svf(D.icy_gridworld_table(n, 0.3), p0, [S - 1], rewards[1])
     assert nn[1] == n_ref
     np.testing.assert_allclose(out[1], ref, rtol=1e-12)
+
+
+@pytest.mark.parametrize("n,p", [(5, 0.2), (24, 0.3)])
+def test_threaded_forward_oracle_is_bitwise_the_serial_loop(n, p):
+    """oracle_svf_mt (OpenMP gather over targets, used for the full-size C3 checks) adds every target's
+    contributions in the order of the serial scatter: same bits, same sweep count."""
+    S = n * n
+    sidx, sp = C.ell_from_sparse(SP.icy_gridworld_sparse(n, p))
+    rng = np.random.default_rng(n)
+    r = -0.1 + 0.05 * rng.standard_normal(S); r[S - 1] = 1.0
+    pol, _, _ = C.soft_vi(sidx, sp, D.terminal_reward([S - 1], S), r, 0.9)
+    p0 = np.zeros(S); p0[0] = 0.5; p0[S // 2] = 0.5
+    for ms in (0, 37):
+        d0, n0 = C.svf(sidx, sp, p0, [S - 1], pol, 1e-5, max_sweeps=ms, threads=False)
+        d1, n1 = C.svf(sidx, sp, p0, [S - 1], pol, 1e-5, max_sweeps=ms, threads=True)
+        assert n0 == n1 and np.array_equal(d0, d1)
+    bad = pol.copy(); bad[3, 1] = np.nan                      # NaN ends both loops on the same sweep
+    d0, n0 = C.svf(sidx, sp, p0, [S - 1], bad, 1e-5, threads=False)
+    d1, n1 = C.svf(sidx, sp, p0, [S - 1], bad, 1e-5, threads=True)
+    assert n0 == n1 and np.array_equal(np.isnan(d0), np.isnan(d1))
