@@ -224,6 +224,26 @@ int irlb200_expected_svf(const irlb200_tables *t, int B, int causal,
                          int32_t *n_iter, int32_t *status, void *stream);
 
 /* ------------------------------------------------------------------------- *
+ * the whole outer gradient loop on the device -- `while delta > eps` of irl (maxent.py:240-252) and
+ * irl_causal (:436-450) -- for tiny worlds (S <= 32, A = 4, 5-slot tables: BASELINE configs[0..1]) with
+ * identity features and a built-in optimizer: one warp per problem runs, per step, the gradient-step body
+ * on reward = omega (:244), grad = e_features - svf (:248), the update rule and the delta test (:252).
+ *   theta  [B][S] in / out (omega);   e_features [B or 1][S]
+ *   opt_kind 0: Sga, omega += lr * grad (optimizer.py:104-107); 1: ExpSga, omega *= exp(lr * grad) (:161-164)
+ *   lr     [B or 1][n_rates] (device): the learning rates of the next n_rates steps -- the schedule
+ *          (optimizer.py:217-293) stays a host-side callable, the host evaluates it ahead
+ *   steps  [B] in / out, accumulated;  done [B] in / out: 1 = delta <= eps or NaN reached (problems that are
+ *          done are skipped); a problem that is not done after n_rates steps needs another call with the
+ *          next rates.  last_counts [B][2] or NULL: {policy sweeps, forward sweeps} of the last step.
+ * ------------------------------------------------------------------------- */
+int irlb200_irl_small(const irlb200_tables *t, int B, int causal, double *theta,
+                      const double *e_features, int ef_shared, const double *p_initial, int p0_shared,
+                      const uint8_t *terminal_mask, const double *phi, int mask_shared,
+                      int n_backward, double discount, double eps_lap, double eps_svf, int max_sweeps,
+                      int opt_kind, const double *lr, int lr_shared, int n_rates, double eps,
+                      int32_t *steps, int32_t *done, int32_t *last_counts, void *stream);
+
+/* ------------------------------------------------------------------------- *
  * slab mode (one huge MDP sharded by contiguous state ranges over several GPUs; the halo
  * exchange and the convergence all-reduce run between launches, see irl-maxent_b200/slab.py).
  * ONE sweep over the owned states [lo, lo+cnt) of a full-length iterate:

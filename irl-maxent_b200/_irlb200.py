@@ -80,6 +80,8 @@ SIGNATURES = {
     "irlb200_svf_ordered": ([_tp, _i, _vp, _i, _vp, _i, _vp, _d, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp], _i),
     "irlb200_expected_svf": ([_tp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _d, _d, _d, _i,
                               _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp], _i),
+    "irlb200_irl_small": ([_tp, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _d, _d, _d, _i, _i, _vp, _i, _i, _d,
+                           _vp, _vp, _vp, _vp], _i),
     "irlb200_sample_trajectories": ([_tp, _vp, _vp, _vp, _i, _i, ctypes.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "irlb200_features_dot": ([_vp, _i, _i, _vp, _vp, _vp], _i),
     "irlb200_features_grad": ([_vp, _i, _i, _vp, _vp, _vp, _vp], _i),
@@ -661,3 +663,34 @@ def features_grad(features, svf_t, e_features):
     out = torch.empty(F, dtype=torch.float64, device=features.device)
     _check(_lib.irlb200_features_grad(_ptr(features), S, F, _ptr(svf_t), _ptr(e_features), _ptr(out), _stream()))
     return out
+
+
+def irl_small(tables, theta, e_features, p_initial, terminal_mask_t, opt_kind, rates, eps, steps, done,
+              causal=False, phi=None, discount=0.0, eps_lap=1e-5, eps_svf=1e-5, n_backward=None, max_sweeps=None):
+    """The outer loop of irl / irl_causal on the device for up to `rates.shape[-1]` steps (see
+    irlb200_irl_small in the header).  theta [B,S], steps [B], done [B] are updated in place;
+    returns the {policy, forward} sweep counts of the last step [B,2]."""
+    torch = require_cuda()
+    S = tables.S
+    B = int(theta.shape[0])
+    ef, efshared = _maybe_shared(e_features, S, B)
+    p0, p0shared = _maybe_shared(p_initial, S, B)
+    mask, mshared = _maybe_shared(terminal_mask_t, S, B, torch.uint8)
+    ph = None
+    if causal:
+        ph, pshared = _maybe_shared(phi, S, B)
+        if pshared != mshared:
+            raise EngineError("phi and terminal mask must both be shared or both per-problem")
+    rates = to_device(rates)
+    lr_shared = 1 if rates.dim() == 1 else 0
+    n_rates = int(rates.shape[-1])
+    counts = torch.zeros((B, 2), dtype=torch.int32, device=theta.device)
+    ct = tables.c_struct(_tables_shared(tables, B))
+    ms = DEFAULT_MAX_SWEEPS if max_sweeps is None else int(max_sweeps)
+    with _timed("irl_small"):
+        _check(_lib.irlb200_irl_small(
+            ctypes.byref(ct), B, 1 if causal else 0, _ptr(theta), _ptr(ef), efshared, _ptr(p0), p0shared, _ptr(mask),
+            _ptr(ph), mshared, 2 * S if n_backward is None else int(n_backward), float(discount), float(eps_lap),
+            float(eps_svf), ms, int(opt_kind), _ptr(rates), lr_shared, n_rates, float(eps), _ptr(steps), _ptr(done),
+            _ptr(counts), _stream()))
+    return counts

@@ -744,3 +744,43 @@ extern "C" int irlb200_expected_svf(const irlb200_tables *t, int B, int causal,
     return causal ? launch_step_cta<true>(bt, B, (cudaStream_t)stream)
                   : launch_step_cta<false>(bt, B, (cudaStream_t)stream);
 }
+
+// The outer loop of irl / irl_causal on the device (tiny worlds, identity features, built-in optimizer).
+extern "C" int irlb200_irl_small(const irlb200_tables *t, int B, int causal, double *theta,
+                                 const double *e_features, int ef_shared, const double *p_initial, int p0_shared,
+                                 const uint8_t *terminal_mask, const double *phi, int mask_shared,
+                                 int n_backward, double discount, double eps_lap, double eps_svf, int max_sweeps,
+                                 int opt_kind, const double *lr, int lr_shared, int n_rates, double eps,
+                                 int32_t *steps, int32_t *done, int32_t *last_counts, void *stream) {
+    if (int rc = check_tables(t, true, true)) return rc;
+    if (B <= 0 || !theta || !e_features || !p_initial || !terminal_mask || !lr || n_rates <= 0 || !steps || !done)
+        return fail(IRLB200_EINVAL, "irl_small: bad argument");
+    if (causal && !phi) return fail(IRLB200_EINVAL, "irl_small: causal needs phi");
+    if (opt_kind != 0 && opt_kind != 1) return fail(IRLB200_EINVAL, "irl_small: optimizer kind must be 0 (Sga) or 1 (ExpSga)");
+    if (device_count_impl() <= 0) return fail(IRLB200_ECUDA, "no CUDA device");
+    if (t->S > 32 || !is_fast_shape(t->A, t->Ks) || !is_fast_shape(t->A, t->Kp))
+        return fail(IRLB200_ELIMIT, "irl_small: needs S <= 32, A = 4 and 5-slot tables");
+    StepBatch bt{};
+    fill_succ(bt.s, t);
+    bt.s.phi = phi; bt.s.term = terminal_mask; bt.s.discount = discount;
+    bt.s.eps = eps_lap; bt.s.n_sweeps = n_backward; bt.s.max_sweeps = max_sweeps;
+    fill_svf(bt.f, t);
+    bt.f.p0 = p_initial; bt.f.term = terminal_mask; bt.f.eps = eps_svf; bt.f.max_sweeps = max_sweeps;
+    bt.f.e_features = e_features;
+    bt.succ_idx_stride = t->shared ? 0 : (size_t)t->Ks * t->S;
+    bt.succ_p_stride = t->shared ? 0 : (size_t)t->A * t->Ks * t->S;
+    bt.pred_idx_stride = t->shared ? 0 : (size_t)t->Kp * t->S;
+    bt.pred_p_stride = t->shared ? 0 : (size_t)t->A * t->Kp * t->S;
+    bt.phi_stride = mask_shared ? 0 : (size_t)t->S;
+    bt.term_stride = mask_shared ? 0 : (size_t)t->S;
+    bt.p0_stride = p0_shared ? 0 : (size_t)t->S;
+    bt.ef_stride = ef_shared ? 0 : (size_t)t->S;
+    IrlLoopArgs lp{};
+    lp.theta = theta; lp.lr = lr; lp.lr_stride = lr_shared ? 0 : (size_t)n_rates; lp.n_rates = n_rates;
+    lp.kind = opt_kind; lp.eps = eps; lp.steps = steps; lp.done = done; lp.last_counts = last_counts;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (causal) irl_warp_kernel<true><<<(B + 3) / 4, 128, 0, st>>>(bt, lp, B);
+    else irl_warp_kernel<false><<<(B + 3) / 4, 128, 0, st>>>(bt, lp, B);
+    LAUNCH_CHECK("irl_warp_kernel");
+    return IRLB200_OK;
+}

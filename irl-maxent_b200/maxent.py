@@ -28,6 +28,8 @@ Differences from the reference, by design:
   * there is no CPU fallback.
 """
 
+import os
+
 import numpy as np
 
 import _irlb200 as E
@@ -163,7 +165,48 @@ def compute_expected_causal_svf(p_transition, p_initial, terminal, reward, disco
 
 # -- outer gradient loops ------------------------------------------------------------
 
-def _irl_loop(p_transition, features, terminal, trajectories, optim, init, eps, step):
+def _builtin_optimizer_kind(optim):
+    """0 / 1 if `optim` is this package's plain Sga / ExpSga (update rule known to irlb200_irl_small), with
+    `step` and `reset` untouched -- a subclass, a wrapper or a patched class keeps the generic host loop."""
+    import optimizer as O
+    t = type(optim)
+    if t is O.Sga and t.step is _SGA_STEP:
+        return 0
+    if t is O.ExpSga and t.step is _EXPSGA_STEP and not optim.normalize:
+        return 1
+    return None
+
+
+def _capture_builtin_steps():
+    import optimizer as O
+    return O.Sga.step, O.ExpSga.step
+
+
+_SGA_STEP, _EXPSGA_STEP = _capture_builtin_steps()
+DEVICE_LOOP_CHUNK = 1024        # learning rates handed to one launch of the device-side outer loop
+
+
+def _irl_device_loop(tables, mask, p_initial_d, e_features_d, theta, optim, kind, eps, causal, phi, discount,
+                     eps_lap, eps_svf):
+    """`while delta > eps` (maxent.py:240-252 / :436-450) inside irlb200_irl_small: the host evaluates the
+    schedule for the next DEVICE_LOOP_CHUNK steps and reads back (steps, done) once per launch."""
+    import optimizer as O
+    torch = E._torch()
+    th = theta.view(1, -1)
+    steps = torch.zeros(1, dtype=torch.int32, device=theta.device)
+    done = torch.zeros(1, dtype=torch.int32, device=theta.device)
+    while True:
+        rates = np.array([O._rate(optim.lr, optim.k + i) for i in range(DEVICE_LOOP_CHUNK)], dtype=np.float64)
+        before = int(steps.item())
+        counts = E.irl_small(tables, th, e_features_d, p_initial_d, mask, kind, rates, eps, steps, done, causal=causal,
+                             phi=phi, discount=discount, eps_lap=eps_lap, eps_svf=eps_svf)
+        optim.k += int(steps.item()) - before            # the optimizer object ends up where the host loop leaves it
+        E.last_info = E.SweepInfo(counts, torch.zeros_like(counts))
+        if int(done.item()):
+            return
+
+
+def _irl_loop(p_transition, features, terminal, trajectories, optim, init, eps, step, device_loop=None):
     """Shared body of irl / irl_causal (reference: maxent.py:229-255, :426-453).
 
     omega (`theta`) lives on the device for the whole optimisation; the optimizer
@@ -186,6 +229,13 @@ def _irl_loop(p_transition, features, terminal, trajectories, optim, init, eps, 
 
     theta = E.to_device(init(n_features))
     optim.reset(theta)
+    kind = _builtin_optimizer_kind(optim)
+    if (device_loop is not None and identity and kind is not None and S <= 32 and tables.A == 4
+            and tables.Ks == 5 and tables.Kp == 5 and tables.n_tables == 1
+            and os.environ.get("IRLB200_DEVICE_LOOP", "1") != "0"):
+        # tiny world, identity features, built-in optimizer: the whole loop in one launch per 1024 steps
+        _irl_device_loop(tables, mask, p_initial_d, e_features_d, theta, optim, kind, eps, **device_loop)
+        return _out(theta.clone(), as_t)
     delta = np.inf
     while delta > eps:
         theta_old = theta.clone()
@@ -210,7 +260,8 @@ def irl(p_transition, features, terminal, trajectories, optim, init, eps=1e-4, e
     def step(tables, p0, mask, reward, ef):
         d, g, _ = E.expected_svf(tables, p0, mask, reward, causal=False, eps_svf=eps_esvf, e_features=ef)
         return d, g
-    return _irl_loop(p_transition, features, terminal, trajectories, optim, init, eps, step)
+    return _irl_loop(p_transition, features, terminal, trajectories, optim, init, eps, step,
+                     device_loop=dict(causal=False, phi=None, discount=0.0, eps_lap=1e-5, eps_svf=eps_esvf))
 
 
 def irl_causal(p_transition, features, terminal, trajectories, optim, init, discount,
@@ -226,7 +277,8 @@ def irl_causal(p_transition, features, terminal, trajectories, optim, init, disc
         d, g, _ = E.expected_svf(tables, p0, mask, reward, causal=True, phi=phi, discount=discount,
                                  eps_lap=eps_lap, eps_svf=eps_svf, e_features=ef)
         return d, g
-    return _irl_loop(p_transition, features, terminal, trajectories, optim, init, eps, step)
+    return _irl_loop(p_transition, features, terminal, trajectories, optim, init, eps, step,
+                     device_loop=dict(causal=True, phi=phi, discount=discount, eps_lap=eps_lap, eps_svf=eps_svf))
 
 
 # -- batched mode (no counterpart in the reference: B independent problems) ------------

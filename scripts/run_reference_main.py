@@ -30,29 +30,26 @@ class _Inert(types.ModuleType):
 
 
 def _count_outer_steps():
-    """IRLB200_MAIN_REPORT=1: count the optimizer steps of every `irl` / `irl_causal` call (one per outer
-    gradient step, maxent.py:251 / :449) by wrapping the ENGINE's optimizer classes -- main.py itself stays
-    untouched -- and print them when the script ends."""
+    """IRLB200_MAIN_REPORT=1: report the outer gradient steps of every `irl` / `irl_causal` call (one optimizer
+    step each, maxent.py:251 / :449).  The ENGINE's optimizer classes remember every instance handed to
+    `reset`; an optimizer's step counter `k` (reference: optimizer.py:33,104) is read when the script ends --
+    it counts the same whether the loop ran on the host or inside irlb200_irl_small.  main.py stays untouched."""
     import atexit
     import optimizer as O
-    runs = []
+    seen = []
 
     def wrap(cls):
-        reset, step = cls.reset, cls.step
+        reset = cls.reset
 
-        def counted_reset(self, parameters):
-            runs.append(0)
+        def recording_reset(self, parameters):
+            seen.append(self)
             return reset(self, parameters)
 
-        def counted_step(self, grad, *a, **k):
-            runs[-1] += 1
-            return step(self, grad, *a, **k)
-
-        cls.reset, cls.step = counted_reset, counted_step
+        cls.reset = recording_reset
 
     for name in ("Sga", "ExpSga"):
         wrap(getattr(O, name))
-    atexit.register(lambda: print("IRLB200_MAIN_OUTER_STEPS %s" % " ".join(str(n) for n in runs), flush=True))
+    atexit.register(lambda: print("IRLB200_MAIN_OUTER_STEPS %s" % " ".join(str(o.k) for o in seen), flush=True))
 
 
 def main(path):

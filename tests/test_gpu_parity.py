@@ -397,6 +397,50 @@ def test_the_reference_main_py_runs_unchanged_on_the_gpu(golden):
     assert steps == [int(g["irl_steps"]), int(g["irl_causal_0.7_steps"])] == [375, 419]
 
 
+@pytest.mark.parametrize("causal,gamma", [(False, None), (True, 0.7), (True, 0.9)])
+@pytest.mark.parametrize("opt", ["expsga_linear", "sga_const", "expsga_power"])
+def test_device_side_outer_loop_equals_the_host_loop(golden, causal, gamma, opt, monkeypatch):
+    """irlb200_irl_small (the whole `while delta > eps` loop in one launch, host-evaluated learning rates)
+    against the generic host loop: bitwise the same reward, the same number of outer steps, the optimizer
+    object left in the same state -- and the reference's own step counts for main.py's settings."""
+    g, P = golden("e2e_5x5"), golden("worlds")["icy_5_0.2"]
+    tjs = load_trajectories(g)
+    F = W.state_features(W.IcyGridWorld(5, 0.2))
+
+    def make():
+        if opt == "expsga_linear":
+            return O.ExpSga(lr=O.linear_decay(lr0=0.2))
+        if opt == "sga_const":
+            return O.Sga(lr=0.05)
+        return O.ExpSga(lr=O.power_decay(lr0=0.3))
+
+    def run(o):
+        if causal:
+            return M.irl_causal(P, F, [24], tjs, o, O.Constant(1.0), gamma)
+        return M.irl(P, F, [24], tjs, o, O.Constant(1.0))
+
+    monkeypatch.setattr(M, "DEVICE_LOOP_CHUNK", 100)             # several launches: the chunk hand-over is exercised
+    dev_opt = make()
+    E.launch_log = []
+    r_dev = run(dev_opt)
+    names = [nm for nm, _, _ in E.launch_log]
+    E.launch_log = None
+    assert names and set(names) == {"irl_small"}, names
+    host_opt = _Count(make())                                    # a wrapper: keeps the generic host loop
+    r_host = run(host_opt)
+    assert np.array_equal(r_dev, r_host, equal_nan=True)
+    assert dev_opt.k == host_opt.n == host_opt.inner.k
+    assert len(names) == (dev_opt.k + 99) // 100
+    if opt == "expsga_linear":
+        key = "irl_steps" if not causal else "irl_causal_%s_steps" % gamma
+        assert dev_opt.k == int(g[key])
+    monkeypatch.setenv("IRLB200_DEVICE_LOOP", "0")               # the switch
+    E.launch_log = []
+    r_off = run(make())
+    assert "irl_small" not in [nm for nm, _, _ in E.launch_log] and np.array_equal(r_off, r_dev, equal_nan=True)
+    E.launch_log = None
+
+
 def test_irl_other_optimizers_and_dense_features(golden):
     g = golden("e2e_5x5")
     world = W.IcyGridWorld(size=5, p_slip=0.2)
