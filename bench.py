@@ -774,6 +774,8 @@ def run_b200_arm(args):
         try:
             c5 = c5_slab(world, rank, dev)
         except Exception as e:                                             # side measurements never sink the line
+            import traceback
+            sys.stderr.write("[rank %d] C5 slab block failed:\n%s\n" % (rank, traceback.format_exc()))
             c5 = {"error": repr(e)}
 
     line = None

@@ -301,7 +301,10 @@ int    irlb200_slab_persistent(int op, int rank, int world, void *const *blocks,
  * owns a fixed range of states and waits only for the CTAs (and, on the slab's first / last grid
  * row, the neighbouring GPU's mailbox) within one grid row of it; the stop rule is all-reduced once per `chunk` sweeps (<= 64; <= 0: default 32) and the
  * exact stopping sweep of the reference (maxent.py:108,326; solver.py:40) is reproduced by
- * snapshot-and-replay inside the kernel.  `work` is a caller-owned device buffer of at least
+ * snapshot-and-replay inside the kernel.  Requirement (true for every GridWorld / IcyGridWorld slab): the
+ * coupling across a slab boundary is one-to-one and symmetric -- a state s in the first / last `halo` states
+ * of a slab links to s -+ halo in the neighbouring slab and to nothing else there, and that state links
+ * back to s; other tables must use irlb200_slab_persistent.  `work` is a caller-owned device buffer of at least
  * irlb200_slab_flow_work_bytes(cnt) bytes, private to this call (not peer-mapped; any contents). */
 size_t irlb200_slab_flow_work_bytes(int cnt);
 /* The peer-mapped block of a rank for irlb200_slab_flow is the block of irlb200_slab_persistent followed by

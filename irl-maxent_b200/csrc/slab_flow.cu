@@ -132,7 +132,13 @@ __global__ void __launch_bounds__(256, MINB)
             if ((spins & 1023u) == 1023u && !keep_waiting(t0)) return false;
         }
     };
-    // iterate number `it` (buffer it & 1, mailbox tag it + 1) at global index g
+    // iterate number `it` (buffer it & 1, mailbox tag it + 1) at global index g.
+    // Mailbox protocol: the slot of iterate `it` is reused by iterate it + 2, and the reader insists on the exact
+    // tag.  That is safe because the coupling across a slab boundary is one-to-one and symmetric in every grid
+    // world (my state s reads the neighbour's s +- halo and nothing else over there, and that state reads s):
+    // the neighbour cannot produce iterate it + 2 of the slot before it has received my iterate it + 1 of s,
+    // which the thread that owns s sends only after it has read the slot.  Tables that couple slabs in any
+    // other way must use irlb200_slab_persistent (slab.PeerSlabGrid(flow=False)).
     auto load_x = [&](const double *x_in, unsigned it, int g) -> double {
         if (g >= lo && g < hi) return ld_cg(x_in + g);
         const LLSlot *slot = g < lo ? my_mail + (size_t)(it & 1u) * h + (g - (lo - h))
@@ -265,10 +271,13 @@ __global__ void __launch_bounds__(256, MINB)
                         p0v[u] = __ldg(a.c0 + i);
                         xo[u] = ld_cg(x_in + lo + i);
                     }
+                    // Only the thread that OWNS a state may read its neighbours: a mailbox slot is overwritten as
+                    // soon as the value computed from it has crossed back (see load_x), so a second reader -- a
+                    // clamped, inactive slot -- could wait for a tag that is already gone.
 #pragma unroll
                     for (int u = 0; u < UU; ++u)
 #pragma unroll
-                        for (int j = 0; j < KK; ++j) xv[u][j] = xl(ix[u][j]);
+                        for (int j = 0; j < KK; ++j) xv[u][j] = (i0 + u * nthr < end) ? xl(ix[u][j]) : 0.0;
 #pragma unroll
                     for (int u = 0; u < UU; ++u) {
                         const int i = i0 + u * nthr;

@@ -1,6 +1,6 @@
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
-for n in 64 128; do
-  timeout 120 $TR scripts/slab_multi_gpu_check.py $n peer 3000 2>&1 | grep "mode=\|parity\|rror" 
+for rep in 1 2 3; do
+timeout 100 $TR scripts/slab_flow_probe.py 2048 0 6000 IRLB200_SLAB_FLOW=1 IRLB200_FLOW_CHUNK=64 2>&1 | grep "^n=\|aborted" | sort | uniq | head -5
 done
-timeout 300 $TR scripts/slab_flow_probe.py 1024 1200 3000 IRLB200_SLAB_FLOW=0 IRLB200_FLOW_FWD=14 IRLB200_FLOW_FWD=24 IRLB200_FLOW_FWD=42 IRLB200_FLOW_EDGE_CTAS=0 IRLB200_FLOW_EDGE_CTAS=8 2>&1 | grep "^n=\|rror"
-timeout 200 $TR scripts/slab_c5_bench.py 2048 300 600 2>&1 | grep "^C5.*peer\|rror"
+timeout 100 $TR scripts/slab_flow_probe.py 1024 600 30000 IRLB200_SLAB_FLOW=1 2>&1 | grep "^n=\|aborted" | sort | uniq | head -5
+timeout 400 $TR scripts/_c5_only.py 2>&1 | grep -v "^\*\*\*\|OMP_NUM\|^$" | tail -70
