@@ -408,7 +408,50 @@ def other_configs():
         out["C2_batched_x1024"] = {"error": repr(e)}
     out["C4_causal_batch"] = causal_batch()
     out["roofline_stream"] = stream_roofline()
+    try:
+        out["dense_batch"] = dense_batch_line()
+    except Exception as e:
+        out["dense_batch"] = {"error": repr(e)}
     return out
+
+
+def dense_batch_line(S=1024, A=4, B=4096, sweeps=24, B_gather=256):
+    """BASELINE configs[3], dense case: B reward candidates over ONE dense random table (K = S successors per
+    state), soft-VI sweeps as FP64 tensor-core contractions [A S x S] . [S x B] (csrc/dense_batch.cu) against the
+    run-time-K ELL gather on the same table (timed on B_gather candidates).  Fixed sweep budget; CUDA events."""
+    import torch
+    import _irlb200 as E
+    rng = np.random.default_rng(5)
+    P = torch.as_tensor(rng.random((S, S, A))).cuda() ** 3
+    P[S - 1] = 0.0
+    P[S - 1, S - 1, :] = 1.0
+    P /= P.sum(dim=1, keepdim=True)
+    rewards = torch.as_tensor(-0.2 + 0.1 * rng.standard_normal((B, S))).cuda()
+    phi = E.terminal_phi([S - 1], S)
+    dt = E.DenseTables(P)
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / 1e3
+
+    t_dense = timed(lambda: E.dense_soft_vi(dt, phi, rewards, 0.9, 1e-30, max_sweeps=sweeps))
+    tabs = E.compress_dense(P)
+    t_gather = timed(lambda: E.soft_vi(tabs, phi, rewards[:B_gather], 0.9, 1e-30, max_sweeps=sweeps))
+    flops = 2.0 * A * S * S * B * sweeps
+    per_cs_dense, per_cs_gather = t_dense / (B * sweeps), t_gather / (B_gather * sweeps)
+    return {"workload": "dense random MDP S=%d A=%d, %d candidates, %d soft-VI sweeps" % (S, A, B, sweeps),
+            "dense_seconds": t_dense, "dense_us_per_sweep_all_candidates": 1e6 * t_dense / sweeps,
+            "dense_TFLOPs_fp64": flops / t_dense / 1e12,
+            "fp64_peak_note": "B200 FP64: 33.6 TFLOP/s measured with DFMA (scripts/ubench.cu), 40 nominal (vector and tensor)",
+            "ell_gather_seconds_for_%d_candidates" % B_gather: t_gather,
+            "ns_per_candidate_sweep": {"dense": 1e9 * per_cs_dense, "ell_gather": 1e9 * per_cs_gather},
+            "speedup_over_ell_gather": per_cs_gather / per_cs_dense}
 
 
 def causal_batch(B=4096, n=32):

@@ -331,6 +331,38 @@ int irlb200_features_grad(const double *features, int S, int F, const double *sv
                           const double *e_features, double *grad, void *stream);
 
 /* ------------------------------------------------------------------------- *
+ * batched DENSE path (BASELINE north_star (4), configs[3]): B reward candidates / policies that share one
+ * dense p_transition.  The reference's sweep is then literally `p[a].dot(X)` for a matrix X [S x B]
+ * (maxent.py:155, :329; `p[a].T.dot(p_action[:, a] * d)`, :109): an FP64 contraction on the tensor cores
+ * (mma.sync m8n8k4 f64) with the elementwise part of the reference as epilogue, every candidate stopped at
+ * its own sweep.  For tables with K ~ S successors per state; sparse worlds belong to the ELL kernels above.
+ *   irlb200_dense_pack: P [S][S'][A] (A innermost, gridworld.py:124-142) -> packed
+ *       [A*S][S] per-action rows | [S][S] action-summed | [S][A*S] transposed   (irlb200_dense_pack_doubles doubles)
+ *   work: caller-owned device buffer of irlb200_dense_batch_work_bytes(S, A, B) bytes, private to the call.
+ *   All [B][...] arrays are candidate-major.  These calls synchronise `stream` (the host polls the number
+ *   of live candidates every few sweeps).
+ *   backward: local_action_probabilities (maxent.py:119-159), n_sweeps partition sweeps (reference: 2 S), exact
+ *       power-of-two rescale per candidate; iterate [B][S] scratch; policy [B][S][A] out
+ *   succ op 1: local_causal_action_probabilities (:279-341), phi [S], value [B][S] out, policy [B][S][A] out
+ *        op 2: value_iteration (solver.py:9-52; vi_mean: :55-104), value [B][S] out, policy unused
+ *   svf: expected_svf_from_policy (:63-114), policy [B][S][A] in, svf [B][S] out, optional grad = e_features - svf
+ * ------------------------------------------------------------------------- */
+size_t irlb200_dense_pack_doubles(int S, int A);
+size_t irlb200_dense_batch_work_bytes(int S, int A, int B);
+int irlb200_dense_pack(const double *P, int S, int A, double *packed, void *stream);
+int irlb200_dense_batch_backward(const double *packed, int S, int A, int B, const double *reward,
+                                 const uint8_t *terminal_mask, int n_sweeps, double *policy, double *iterate,
+                                 void *work, size_t work_bytes, void *stream);
+int irlb200_dense_batch_succ(int op, const double *packed, int S, int A, int B, const double *reward,
+                             const double *phi, double discount, double eps, int max_sweeps, int vi_mean,
+                             double *value, double *policy, int32_t *n_iter, int32_t *status, void *work,
+                             size_t work_bytes, void *stream);
+int irlb200_dense_batch_svf(const double *packed, int S, int A, int B, const double *p_initial, int p0_shared,
+                            const uint8_t *terminal_mask, const double *policy, double eps, int max_sweeps,
+                            double *svf, const double *e_features, int ef_shared, double *grad,
+                            int32_t *n_iter, int32_t *status, void *work, size_t work_bytes, void *stream);
+
+/* ------------------------------------------------------------------------- *
  * expert demonstrations on the device
  *   replaces trajectory.generate_trajectories / generate_trajectory, trajectory.py:52-128, whose
  *   per-step `np.random.choice` over the dense row p_transition[s, :, a] is O(S) and needs a table

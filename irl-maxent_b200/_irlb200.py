@@ -80,6 +80,14 @@ SIGNATURES = {
     "irlb200_svf_ordered": ([_tp, _i, _vp, _i, _vp, _i, _vp, _d, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp], _i),
     "irlb200_expected_svf": ([_tp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _d, _d, _d, _i,
                               _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp], _i),
+    "irlb200_dense_pack_doubles": ([_i, _i], ctypes.c_size_t),
+    "irlb200_dense_batch_work_bytes": ([_i, _i, _i], ctypes.c_size_t),
+    "irlb200_dense_pack": ([_vp, _i, _i, _vp, _vp], _i),
+    "irlb200_dense_batch_backward": ([_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, ctypes.c_size_t, _vp], _i),
+    "irlb200_dense_batch_succ": ([_i, _vp, _i, _i, _i, _vp, _vp, _d, _d, _i, _i, _vp, _vp, _vp, _vp, _vp,
+                                  ctypes.c_size_t, _vp], _i),
+    "irlb200_dense_batch_svf": ([_vp, _i, _i, _i, _vp, _i, _vp, _vp, _d, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp,
+                                 ctypes.c_size_t, _vp], _i),
     "irlb200_irl_small": ([_tp, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _d, _d, _d, _i, _i, _vp, _i, _i, _d,
                            _vp, _vp, _vp, _vp], _i),
     "irlb200_sample_trajectories": ([_tp, _vp, _vp, _vp, _i, _i, ctypes.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
@@ -694,3 +702,114 @@ def irl_small(tables, theta, e_features, p_initial, terminal_mask_t, opt_kind, r
             float(eps_svf), ms, int(opt_kind), _ptr(rates), lr_shared, n_rates, float(eps), _ptr(steps), _ptr(done),
             _ptr(counts), _stream()))
     return counts
+
+
+# ---------------------------------------------------------------------------
+# batched dense path: B candidates sharing one dense table (csrc/dense_batch.cu)
+# ---------------------------------------------------------------------------
+
+class DenseTables:
+    """A dense p_transition[S, S', A] packed for the FP64 tensor-core contraction (irlb200_dense_pack)."""
+
+    def __init__(self, p_transition):
+        torch = require_cuda()
+        P = to_device(p_transition)
+        if P.dim() != 3 or P.shape[0] != P.shape[1]:
+            raise EngineError("p_transition must have shape [S, S, A]")
+        self.S, self.A = int(P.shape[0]), int(P.shape[2])
+        self.packed = torch.empty(int(_lib.irlb200_dense_pack_doubles(self.S, self.A)), dtype=torch.float64,
+                                  device=P.device)
+        _check(_lib.irlb200_dense_pack(_ptr(P), self.S, self.A, _ptr(self.packed), _stream()))
+        self._work = None
+
+    @property
+    def shape(self):
+        return (self.S, self.S, self.A)
+
+    def work(self, B):
+        torch = _torch()
+        need = int(_lib.irlb200_dense_batch_work_bytes(self.S, self.A, B))
+        if self._work is None or self._work.numel() < need:
+            self._work = torch.empty(need, dtype=torch.uint8, device=self.packed.device)
+        return self._work
+
+
+def dense_backward(dt, terminal_mask_t, reward, n_sweeps=None):
+    """local_action_probabilities for B candidates over a shared dense table: policy [B, S, A]."""
+    torch = require_cuda()
+    r, B = _batch2d(reward, dt.S)
+    mask = to_device(terminal_mask_t, torch.uint8)
+    pol = torch.empty((B, dt.S, dt.A), dtype=torch.float64, device=r.device)
+    it = torch.empty((B, dt.S), dtype=torch.float64, device=r.device)
+    w = dt.work(B)
+    with _timed("dense_backward"):
+        _check(_lib.irlb200_dense_batch_backward(_ptr(dt.packed), dt.S, dt.A, B, _ptr(r), _ptr(mask),
+                                                 2 * dt.S if n_sweeps is None else int(n_sweeps), _ptr(pol), _ptr(it),
+                                                 _ptr(w), w.numel(), _stream()))
+    return pol
+
+
+def dense_soft_vi(dt, phi, reward, discount, eps=1e-5, max_sweeps=None):
+    """local_causal_action_probabilities for B candidates: (policy [B, S, A], value [B, S])."""
+    global last_info
+    torch = require_cuda()
+    r, B = _batch2d(reward, dt.S)
+    ph = to_device(phi)
+    pol = torch.empty((B, dt.S, dt.A), dtype=torch.float64, device=r.device)
+    val = torch.empty((B, dt.S), dtype=torch.float64, device=r.device)
+    n_iter = torch.zeros(B, dtype=torch.int32, device=r.device)
+    status = torch.zeros(B, dtype=torch.int32, device=r.device)
+    w = dt.work(B)
+    ms = DEFAULT_MAX_SWEEPS if max_sweeps is None else int(max_sweeps)
+    with _timed("dense_soft_vi"):
+        _check(_lib.irlb200_dense_batch_succ(1, _ptr(dt.packed), dt.S, dt.A, B, _ptr(r), _ptr(ph), float(discount),
+                                             float(eps), ms, 0, _ptr(val), _ptr(pol), _ptr(n_iter), _ptr(status),
+                                             _ptr(w), w.numel(), _stream()))
+    last_info = SweepInfo(n_iter, status)
+    return pol, val
+
+
+def dense_value_iteration(dt, reward, discount, eps=1e-3, max_sweeps=None, mean=False):
+    global last_info
+    torch = require_cuda()
+    r, B = _batch2d(reward, dt.S)
+    val = torch.empty((B, dt.S), dtype=torch.float64, device=r.device)
+    n_iter = torch.zeros(B, dtype=torch.int32, device=r.device)
+    status = torch.zeros(B, dtype=torch.int32, device=r.device)
+    w = dt.work(B)
+    ms = DEFAULT_MAX_SWEEPS if max_sweeps is None else int(max_sweeps)
+    with _timed("dense_value_iteration"):
+        _check(_lib.irlb200_dense_batch_succ(2, _ptr(dt.packed), dt.S, dt.A, B, _ptr(r), None, float(discount),
+                                             float(eps), ms, 1 if mean else 0, _ptr(val), None, _ptr(n_iter),
+                                             _ptr(status), _ptr(w), w.numel(), _stream()))
+    last_info = SweepInfo(n_iter, status)
+    return val
+
+
+def dense_svf(dt, p_initial, terminal_mask_t, policy, eps=1e-5, max_sweeps=None, e_features=None):
+    """expected_svf_from_policy for B policies [B, S, A] over a shared dense table."""
+    global last_info
+    torch = require_cuda()
+    pol = to_device(policy)
+    if pol.dim() == 2:
+        pol = pol.unsqueeze(0)
+    B = int(pol.shape[0])
+    if tuple(pol.shape[1:]) != (dt.S, dt.A):
+        raise EngineError("policy must have shape [S, A] or [B, S, A]")
+    p0, p0shared = _maybe_shared(p_initial, dt.S, B)
+    mask = to_device(terminal_mask_t, torch.uint8)
+    out = torch.empty((B, dt.S), dtype=torch.float64, device=pol.device)
+    grad, ef, efshared = None, None, 1
+    if e_features is not None:
+        ef, efshared = _maybe_shared(e_features, dt.S, B)
+        grad = torch.empty((B, dt.S), dtype=torch.float64, device=pol.device)
+    n_iter = torch.zeros(B, dtype=torch.int32, device=pol.device)
+    status = torch.zeros(B, dtype=torch.int32, device=pol.device)
+    w = dt.work(B)
+    ms = DEFAULT_MAX_SWEEPS if max_sweeps is None else int(max_sweeps)
+    with _timed("dense_svf"):
+        _check(_lib.irlb200_dense_batch_svf(_ptr(dt.packed), dt.S, dt.A, B, _ptr(p0), p0shared, _ptr(mask), _ptr(pol),
+                                            float(eps), ms, _ptr(out), _ptr(ef), efshared, _ptr(grad), _ptr(n_iter),
+                                            _ptr(status), _ptr(w), w.numel(), _stream()))
+    last_info = SweepInfo(n_iter, status)
+    return (out, grad) if grad is not None else out

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libirlmaxent_b200.so")
 SOURCES = ["host_util.cu", "tables.cu", "sweep_kernels.cu", "slab_kernels.cu", "slab_persistent.cu",
-           "slab_flow.cu", "trajectories.cu"]
+           "slab_flow.cu", "dense_batch.cu", "trajectories.cu"]
 HEADERS = ["common.cuh", "topo.cuh", "phases.cuh", "host_util.h", "batch_args.cuh", "kernels_cta.cuh",
            "kernels_tiled.cuh", "kernels_cluster.cuh", "slab_common.cuh",
            os.path.join("..", "..", "include", "irl_maxent_b200.h")]

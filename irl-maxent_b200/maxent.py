@@ -299,6 +299,30 @@ def compute_expected_svf_batch(tables, p_initial, terminal, reward, eps=1e-5, ca
     return d, g
 
 
+def compute_expected_svf_dense_batch(p_transition, p_initial, terminal, reward, eps=1e-5, causal=False,
+                                     discount=None, eps_lap=1e-5, e_features=None, max_sweeps=None):
+    """B reward candidates over ONE dense p_transition[S, S', A] (BASELINE configs[3], dense case): the
+    gradient-step body of every candidate as FP64 tensor-core contractions [rows x S] . [S x B]
+    (csrc/dense_batch.cu) -- for tables that really are dense (K ~ S); sparse worlds are faster through
+    `compute_expected_svf_batch`.  `p_transition`: dense array / tensor or a prepared `_irlb200.DenseTables`.
+    reward [B, S]; returns (svf [B, S], grad or None); per-candidate sweep counts in `_irlb200.last_info`."""
+    torch = E.require_cuda()
+    dt = p_transition if isinstance(p_transition, E.DenseTables) else E.DenseTables(p_transition)
+    mask = E.terminal_mask(terminal, dt.S)
+    if causal:
+        pol, _ = E.dense_soft_vi(dt, E.terminal_phi(terminal, dt.S), reward, discount, eps_lap, max_sweeps)
+        info_a = E.last_info
+    else:
+        pol = E.dense_backward(dt, mask, reward)
+        info_a = None
+    res = E.dense_svf(dt, p_initial, mask, pol, eps, max_sweeps, e_features)
+    n_fw, st_fw = E.last_info.n_iter, E.last_info.status
+    n_pol = info_a.n_iter if causal else torch.full_like(n_fw, 2 * dt.S)
+    st_pol = info_a.status if causal else torch.zeros_like(st_fw)
+    E.last_info = E.SweepInfo(torch.stack([n_pol, n_fw], 1), torch.stack([st_pol, st_fw], 1))
+    return res if e_features is not None else (res, None)
+
+
 def irl_batch(tables, terminal, e_features, p_initial, optims, init, eps=1e-4, eps_esvf=1e-5,
               causal=False, discount=None, eps_lap=1e-5, max_steps=None):
     """B independent IRL problems with identity features, run in lockstep on one GPU

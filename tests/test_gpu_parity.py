@@ -1180,3 +1180,66 @@ def test_compress_dense_at_c3_size():
     assert a.k_discovered == (4, 4) and (a.Ks, a.Kp) == (5, 5) and a.stencil_n == n
     for x, y in ((a.succ_idx, b.succ_idx), (a.succ_p, b.succ_p), (a.pred_idx, b.pred_idx), (a.pred_p, b.pred_p)):
         assert (x == y).all()
+
+
+# ------------------------------------------------------------------ dense batch ---
+
+def _dense_random_mdp(rng, S, A, absorbing):
+    P = rng.random((S, S, A)) ** 3                      # dense, skewed: every state reaches every state
+    P[absorbing, :, :] = 0.0
+    P[absorbing, absorbing, :] = 1.0
+    P /= P.sum(axis=1, keepdims=True)
+    return P
+
+
+@pytest.mark.parametrize("S,A,B", [(64, 4, 5), (200, 3, 70), (256, 4, 33)])
+def test_dense_batch_path_against_the_dense_oracle(S, A, B):
+    """BASELINE north_star (4): B candidates sharing a DENSE table as FP64 tensor-core contractions
+    (csrc/dense_batch.cu).  Against oracle/dense_port.py (the reference's arithmetic) candidate by candidate:
+    1e-10 on policies, values and SVF, identical sweep counts; and against the ELL kernels on the same table."""
+    rng = np.random.default_rng(S + B)
+    term = S - 1
+    P = _dense_random_mdp(rng, S, A, term)
+    dt = E.DenseTables(P)
+    rewards = -0.2 + 0.1 * rng.standard_normal((B, S))
+    rewards[:, term] = 0.5
+    p0 = rng.random(S); p0 /= p0.sum()
+    mask = E.terminal_mask([term], S)
+    check = sorted(set([0, B // 2, B - 1]))
+    # soft-VI
+    pol, val = E.dense_soft_vi(dt, E.terminal_phi([term], S), rewards, 0.9, 1e-6)
+    n_lap = counts().copy()
+    for b in check:
+        pref, k = D.local_causal_action_probabilities(P, [term], rewards[b], 0.9, 1e-6)
+        assert n_lap[b] == k
+        close(pol[b], pref)
+    # forward pass of those policies
+    d = E.dense_svf(dt, p0, mask, pol, 1e-7)
+    n_fw = counts().copy()
+    for b in check:
+        dref, k = D.expected_svf_from_policy(P, p0, [term], pol[b].cpu().numpy(), 1e-7)
+        assert n_fw[b] == k
+        close(d[b], dref)
+    # backward pass (rewards near -ln S keep the raw reference finite) and value iteration
+    rb = -np.log(A) + 0.01 * rng.standard_normal((B, S))
+    pb = E.dense_backward(dt, mask, rb)
+    for b in check:
+        close(pb[b], D.local_action_probabilities(P, [term], rb[b], rescale=True))
+        np.testing.assert_allclose(pb[b].cpu().numpy().sum(axis=1), 1.0, rtol=1e-12)
+    v = E.dense_value_iteration(dt, rewards, 0.8, 1e-6)
+    n_vi = counts().copy()
+    for b in check:
+        vref, k = D.value_iteration(P, rewards[b], 0.8, 1e-6)
+        assert n_vi[b] == k
+        close(v[b], vref)
+    # the ELL kernels (run-time K = S gather) on the same dense table: same counts, 1e-10
+    t = E.compress_dense(P)
+    pol_e = E.soft_vi(t, E.terminal_phi([term], S), rewards[check], 0.9, 1e-6)
+    assert (counts() == n_lap[check]).all()
+    close(pol_e, pol[check].cpu().numpy())
+    # module API, with the fused gradient epilogue
+    ef = rng.random(S)
+    svf, grad = M.compute_expected_svf_dense_batch(P, p0, [term], rewards, eps=1e-7, causal=True, discount=0.9,
+                                                   eps_lap=1e-6, e_features=ef)
+    assert (svf == d).all() and (grad == E.to_device(ef) - svf).all()
+    assert (counts()[:, 0] == n_lap).all() and (counts()[:, 1] == n_fw).all()
