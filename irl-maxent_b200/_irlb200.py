@@ -446,11 +446,31 @@ class _timed:
 # entry-point wrappers (device tensors in, device tensors out)
 # ---------------------------------------------------------------------------
 
+ELIMIT = -3
+
+
+def _row(x, b, shared):
+    return x if shared else x[b]
+
+
+def _too_large_for_a_batch(tables, B, mode):
+    """A batch of problems that do not fit one CTA's shared memory (S above ~14 500; soft-VI / VI at the C3 size)
+    cannot run as one launch: the cooperative-grid and cluster modes take one problem per call.  The wrappers
+    then run the batch as B single-problem launches (same results, per-problem counts)."""
+    if B <= 1 or mode == MODE_CTA:
+        return False
+    return (2 * tables.S + 34) * 8 > 227 * 1024
+
+
 def backward(tables, terminal_mask_t, reward, n_sweeps=None, mode=MODE_AUTO):
     """(2) local_action_probabilities, maxent.py:119-159.  reward [S] or [B,S]."""
     torch = require_cuda()
     S, A = tables.S, tables.A
     r, B = _batch2d(reward, S)
+    if _too_large_for_a_batch(tables, B, mode) and not (tables.stencil_n and tables.stencil_n <= 128):
+        mask, mshared = _maybe_shared(terminal_mask_t, S, B, torch.uint8)
+        return torch.cat([backward(tables if tables.n_tables == 1 else tables.select(b), _row(mask, b, mshared), r[b],
+                                   n_sweeps, mode) for b in range(B)], 0)
     mask, mshared = _maybe_shared(terminal_mask_t, S, B, torch.uint8)
     pol = torch.empty((B, S, A), dtype=torch.float64, device=r.device)
     ct = tables.c_struct(_tables_shared(tables, B))
@@ -467,6 +487,16 @@ def soft_vi(tables, phi, reward, discount, eps=1e-5, max_sweeps=None, mode=MODE_
     S, A = tables.S, tables.A
     r, B = _batch2d(reward, S)
     ph, pshared = _maybe_shared(phi, S, B)
+    if _too_large_for_a_batch(tables, B, mode):
+        outs, infos = [], []
+        for b in range(B):
+            outs.append(soft_vi(tables if tables.n_tables == 1 else tables.select(b), _row(ph, b, pshared), r[b],
+                                discount, eps, max_sweeps, mode, want_value))
+            infos.append(last_info)
+        last_info = SweepInfo(torch.cat([i.n_iter for i in infos]), torch.cat([i.status for i in infos]))
+        if want_value:
+            return torch.cat([o[0] for o in outs], 0), torch.cat([o[1] for o in outs], 0)
+        return torch.cat(outs, 0)
     pol = torch.empty((B, S, A), dtype=torch.float64, device=r.device)
     val = torch.empty((B, S), dtype=torch.float64, device=r.device) if want_value else None
     n_iter = torch.empty(B, dtype=torch.int32, device=r.device)      # always written by the kernel
@@ -486,6 +516,14 @@ def value_iteration(tables, reward, discount, eps=1e-3, max_sweeps=None, mean=Fa
     torch = require_cuda()
     S = tables.S
     r, B = _batch2d(reward, S)
+    if _too_large_for_a_batch(tables, B, mode):
+        outs, infos = [], []
+        for b in range(B):
+            outs.append(value_iteration(tables if tables.n_tables == 1 else tables.select(b), r[b], discount, eps,
+                                        max_sweeps, mean, mode))
+            infos.append(last_info)
+        last_info = SweepInfo(torch.cat([i.n_iter for i in infos]), torch.cat([i.status for i in infos]))
+        return torch.cat(outs, 0)
     val = torch.empty((B, S), dtype=torch.float64, device=r.device)
     n_iter = torch.empty(B, dtype=torch.int32, device=r.device)      # always written by the kernel
     status = torch.empty(B, dtype=torch.int32, device=r.device)
@@ -527,6 +565,19 @@ def svf(tables, p_initial, terminal_mask_t, policy, eps=1e-5, max_sweeps=None, e
         raise EngineError("policy must have shape [S, A] or [B, S, A]")
     p0, p0shared = _maybe_shared(p_initial, S, B)
     mask, mshared = _maybe_shared(terminal_mask_t, S, B, torch.uint8)
+    clusterable = tables.stencil_n and tables.stencil_n <= 128 and tables.stencil_n % 4 == 0 and tables.Kp == 5
+    if _too_large_for_a_batch(tables, B, mode) and not clusterable:
+        ef_s = _maybe_shared(e_features, S, B) if e_features is not None else (None, 1)
+        outs, infos = [], []
+        for b in range(B):
+            outs.append(svf(tables if tables.n_tables == 1 else tables.select(b), _row(p0, b, p0shared),
+                            _row(mask, b, mshared), pol[b], eps, max_sweeps,
+                            None if e_features is None else _row(ef_s[0], b, ef_s[1]), mode, None))
+            infos.append(last_info)
+        last_info = SweepInfo(torch.cat([i.n_iter for i in infos]), torch.cat([i.status for i in infos]))
+        if e_features is not None:
+            return torch.cat([o[0] for o in outs], 0), torch.cat([o[1] for o in outs], 0)
+        return torch.cat(outs, 0)
     out = torch.empty((B, S), dtype=torch.float64, device=pol.device)
     grad, ef, efshared = None, None, 1
     if e_features is not None:

@@ -55,11 +55,7 @@ __global__ void dense_pack_kernel(const double *__restrict__ P, int S, int A, do
 // ---------------------------------------------------------------------------
 // FP64 tensor-core GEMM:  Ct[n][m] = sum_k A[m][k] * Xt[n][k]     (A: M x K row-major, Xt: N x K row-major)
 // ---------------------------------------------------------------------------
-constexpr int kTM = 64, kTN = 64, kTK = 16, kStages = 3;
-constexpr int kKbStride = 64 * 4 + 4;                              // doubles per k-block of a 64-row tile (+4: the four
-                                                                   // k-blocks a row is copied into start 8 banks apart)
-constexpr int kOperandDoubles = (kTK / 4) * kKbStride;
-constexpr int kTileDoubles = 2 * kOperandDoubles;                  // one stage: A tile + X tile
+constexpr int kTK = 16, kStages = 3;
 
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem, bool pred) {
     const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem);
@@ -75,26 +71,45 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, const double
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// rows [row0, row0 + 64) x k [k0, k0 + 16) of a row-major matrix (ld = K) -> smem [kb 0..3][row 0..63][4] (kb stride padded)
+// CTA tile = (32 WM) x (32 WN), one warp per 32 x 32 sub-tile (4 x 4 MMA tiles, 32 accumulators per thread).
+//   <2, 2>: 64 x 64, 128 threads, 4 CTAs per SM   -- small problems (many CTAs)
+//   <4, 4>: 128 x 128, 512 threads, 1 CTA per SM  -- 16 flop per byte fetched from L2 instead of 8: the 64 x 64
+//           tile moves ~69 B per clock and SM from L2 at full MMA rate, which is what bounds it
+template <int WM, int WN>
+struct GemmCfg {
+    static constexpr int TM = 32 * WM, TN = 32 * WN, THREADS = 32 * WM * WN;
+    // shared layout of one operand tile: [k-block of 4][row][4], k-block stride padded by 4 doubles so that the
+    // four k-blocks a copied row lands in start 8 banks apart
+    static constexpr int KBS_A = TM * 4 + 4, KBS_X = TN * 4 + 4;
+    static constexpr int A_DOUBLES = (kTK / 4) * KBS_A, X_DOUBLES = (kTK / 4) * KBS_X;
+    static constexpr int STAGE_DOUBLES = A_DOUBLES + X_DOUBLES;
+    static constexpr size_t SMEM = sizeof(double) * kStages * STAGE_DOUBLES;
+};
+
+// rows [row0, row0 + ROWS) x k [k0, k0 + 16) of a row-major matrix (ld = K) -> smem [kb 0..3][row][4]
+template <int ROWS, int THREADS>
 __device__ __forceinline__ void load_tile(double *dst, const double *__restrict__ src, int rows, int K, int row0,
                                           int k0, int tid) {
+    constexpr int KBS = ROWS * 4 + 4;
 #pragma unroll
-    for (int it = 0; it < (64 * kTK) / 128; ++it) {
-        const int e = it * 128 + tid;                              // element of the tile, k fastest
+    for (int it = 0; it < (ROWS * kTK) / THREADS; ++it) {
+        const int e = it * THREADS + tid;                          // element of the tile, k fastest
         const int r = e / kTK, k = e % kTK;
         const bool ok = (row0 + r) < rows && (k0 + k) < K;
         const double *g = src + (ok ? ((size_t)(row0 + r) * K + k0 + k) : 0);
-        cp_async8(dst + (k >> 2) * kKbStride + r * 4 + (k & 3), g, ok);
+        cp_async8(dst + (k >> 2) * KBS + r * 4 + (k & 3), g, ok);
     }
 }
 
-__global__ void __launch_bounds__(128, 4)
+template <int WM, int WN>
+__global__ void __launch_bounds__(32 * WM * WN, (WM * WN <= 4) ? 4 : 1)
     dense_gemm_kernel(const double *__restrict__ Am, const double *__restrict__ Xt, double *__restrict__ Ct, int M,
                       int N, int K) {
+    using Cfg = GemmCfg<WM, WN>;
     extern __shared__ __align__(16) double smem_d[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 1, wn = warp & 1;                       // 2 x 2 warps, 32 x 32 each
-    const int m0 = blockIdx.x * kTM, n0 = blockIdx.y * kTN;
+    const int wm = warp / WN, wn = warp % WN;
+    const int m0 = blockIdx.x * Cfg::TM, n0 = blockIdx.y * Cfg::TN;
     const int nk = (K + kTK - 1) / kTK;
     double acc[4][4][2];
 #pragma unroll
@@ -102,12 +117,12 @@ __global__ void __launch_bounds__(128, 4)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    auto stage = [&](int s) { return smem_d + (size_t)s * kTileDoubles; };
+    auto stage = [&](int s) { return smem_d + (size_t)s * Cfg::STAGE_DOUBLES; };
     auto issue = [&](int kc) {
         if (kc < nk) {
             double *st = stage(kc % kStages);
-            load_tile(st, Am, M, K, m0, kc * kTK, tid);
-            load_tile(st + kOperandDoubles, Xt, N, K, n0, kc * kTK, tid);
+            load_tile<Cfg::TM, Cfg::THREADS>(st, Am, M, K, m0, kc * kTK, tid);
+            load_tile<Cfg::TN, Cfg::THREADS>(st + Cfg::A_DOUBLES, Xt, N, K, n0, kc * kTK, tid);
         }
         cp_async_commit();
     };
@@ -117,14 +132,14 @@ __global__ void __launch_bounds__(128, 4)
         issue(kc + 2);
         cp_async_wait<2>();
         __syncthreads();
-        const double *As = stage(kc % kStages), *Xs = As + kOperandDoubles;
+        const double *As = stage(kc % kStages), *Xs = As + Cfg::A_DOUBLES;
 #pragma unroll
         for (int kb = 0; kb < kTK / 4; ++kb) {
             double af[4], bf[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) af[i] = As[kb * kKbStride + (wm * 32 + i * 8) * 4 + lane];
+            for (int i = 0; i < 4; ++i) af[i] = As[kb * Cfg::KBS_A + (wm * 32 + i * 8) * 4 + lane];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = Xs[kb * kKbStride + (wn * 32 + j * 8) * 4 + lane];
+            for (int j = 0; j < 4; ++j) bf[j] = Xs[kb * Cfg::KBS_X + (wn * 32 + j * 8) * 4 + lane];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -146,18 +161,31 @@ __global__ void __launch_bounds__(128, 4)
     }
 }
 
-static int launch_gemm(const double *Am, const double *Xt, double *Ct, int M, int N, int K, cudaStream_t st) {
+template <int WM, int WN>
+static int launch_gemm_cfg(const double *Am, const double *Xt, double *Ct, int M, int N, int K, cudaStream_t st) {
+    using Cfg = GemmCfg<WM, WN>;
     static bool attr_set = false;
-    const size_t smem = sizeof(double) * kStages * kTileDoubles;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(dense_gemm_kernel<WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
         if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(dense gemm)");
         attr_set = true;
     }
-    dim3 grid((M + kTM - 1) / kTM, (N + kTN - 1) / kTN);
-    dense_gemm_kernel<<<grid, 128, smem, st>>>(Am, Xt, Ct, M, N, K);
+    dim3 grid((M + Cfg::TM - 1) / Cfg::TM, (N + Cfg::TN - 1) / Cfg::TN);
+    dense_gemm_kernel<WM, WN><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(Am, Xt, Ct, M, N, K);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? IRLB200_OK : fail_cuda(e, "dense_gemm_kernel");
+}
+
+static int launch_gemm(const double *Am, const double *Xt, double *Ct, int M, int N, int K, cudaStream_t st) {
+    static int force = -1;
+    if (force < 0) {
+        const char *v = getenv("IRLB200_DENSE_TILE");              // 128: the 128 x 128 tile (experiments)
+        force = v ? atoi(v) : 0;
+    }
+    // measured at S = 1024, A = 4, B = 4096 (soft-VI sweeps): 64 x 64 tiles 18.4 TFLOP/s, 128 x 128 tiles 17.1 --
+    // the small tile's four CTAs per SM hide more latency than the big tile saves in L2 traffic
+    if (force == 128) return launch_gemm_cfg<4, 4>(Am, Xt, Ct, M, N, K, st);
+    return launch_gemm_cfg<2, 2>(Am, Xt, Ct, M, N, K, st);
 }
 
 // ---------------------------------------------------------------------------

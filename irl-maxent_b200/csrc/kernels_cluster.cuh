@@ -41,13 +41,16 @@ __device__ __forceinline__ void svf_grid5_cluster_sweep(unsigned char *smem, uin
 
 // cluster-wide OR of a per-thread predicate: stamp, barrier.cluster, compare.  `word` points at this
 // CTA's vote words [2]; every CTA's copy is written by every voting warp (one lane per target CTA).
+// Stamps only grow, and a CTA goes on to write a LARGER stamp into the same word only after it has seen
+// this vote come out true (a false vote ends the loop or goes to the other word first) -- so a thread that
+// reads the word late and finds a newer stamp knows this vote was true: compare with >=, not ==.
 __device__ __forceinline__ bool cluster_any(cgx::cluster_group &cl, int *word, int stamp, bool pred, int ncta) {
     int *slot = word + (stamp & 1);
     const unsigned any = __ballot_sync(0xffffffffu, pred);
     const int lane = threadIdx.x & 31;
     if (any && lane < ncta) *cl.map_shared_rank(slot, lane) = stamp;
     cl.sync();
-    return *slot == stamp;
+    return *(volatile int *)slot >= stamp;
 }
 
 template <int TY, int TX, int MAXT>

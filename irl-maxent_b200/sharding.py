@@ -53,12 +53,21 @@ def compute_expected_svf_batch_sharded(size, p_slips, p_initial, terminal, rewar
     rank, world = _rank_world(group)
     B = len(p_slips)
     b0, b1 = shard_range(B, rank, world)
-    tabs = E.gridworld_tables(size, np.asarray(p_slips)[b0:b1])
     ef = kwargs.pop("e_features", None)
     if ef is not None and getattr(ef, "ndim", 1) == 2:
         ef = ef[b0:b1]
-    d, g = M.compute_expected_svf_batch(tabs, p_initial, terminal, np.asarray(rewards)[b0:b1], e_features=ef,
-                                        **kwargs)
+    if getattr(p_initial, "ndim", 1) == 2:                       # per-world start distributions: this rank's rows
+        p_initial = p_initial[b0:b1]
+    if b1 == b0:
+        # more ranks than worlds: this rank has nothing to run, but still takes part in the gather
+        torch = E.require_cuda()
+        S = size * size
+        d = torch.zeros((0, S), dtype=torch.float64, device=E._dev())
+        g = torch.zeros((0, S), dtype=torch.float64, device=E._dev()) if ef is not None else None
+    else:
+        tabs = E.gridworld_tables(size, np.asarray(p_slips)[b0:b1])
+        d, g = M.compute_expected_svf_batch(tabs, p_initial, terminal, np.asarray(rewards)[b0:b1], e_features=ef,
+                                            **kwargs)
     if gather:
         d = gather_rows(d, B, group)
         g = gather_rows(g, B, group) if g is not None else None

@@ -1243,3 +1243,22 @@ def test_dense_batch_path_against_the_dense_oracle(S, A, B):
                                                    eps_lap=1e-6, e_features=ef)
     assert (svf == d).all() and (grad == E.to_device(ef) - svf).all()
     assert (counts()[:, 0] == n_lap).all() and (counts()[:, 1] == n_fw).all()
+
+
+def test_batches_of_worlds_too_large_for_one_cta():
+    """a batch of problems beyond one CTA's shared memory (the C3 size) used to fail with ELIMIT in
+    soft-VI / VI; the wrappers now run it as single-problem launches with the same results and counts."""
+    n = 128
+    S = n * n
+    tabs = E.gridworld_tables(n, [0.2, 0.3])
+    r = np.stack([np.full(S, -0.1), np.full(S, -0.2)]); r[:, S - 1] = 1.0
+    phi = E.terminal_phi([S - 1], S)
+    pol = E.soft_vi(tabs, phi, r, 0.9)
+    n_b = counts().copy()
+    for b in range(2):
+        one = E.soft_vi(tabs.select(b), phi, r[b], 0.9)
+        assert counts()[0] == n_b[b] and (one[0] == pol[b]).all()
+    v = E.value_iteration(tabs, r, 0.9, 1e-4)
+    assert v.shape == (2, S) and (counts() > 10).all()
+    d, g = M.compute_expected_svf_batch(tabs, np.eye(S)[0], [S - 1], r, causal=True, discount=0.9, max_sweeps=3000)
+    assert d.shape == (2, S) and (counts()[:, 0] == n_b).all() and (counts()[:, 1] == 3000).all()
