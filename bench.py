@@ -445,10 +445,14 @@ def dense_batch_line(S=1024, A=4, B=4096, sweeps=24, B_gather=256):
     t_gather = timed(lambda: E.soft_vi(tabs, phi, rewards[:B_gather], 0.9, 1e-30, max_sweeps=sweeps))
     flops = 2.0 * A * S * S * B * sweeps
     per_cs_dense, per_cs_gather = t_dense / (B * sweeps), t_gather / (B_gather * sweeps)
+    ncu = ncu_constants().get("dense_gemm_kernel", {})
     return {"workload": "dense random MDP S=%d A=%d, %d candidates, %d soft-VI sweeps" % (S, A, B, sweeps),
             "dense_seconds": t_dense, "dense_us_per_sweep_all_candidates": 1e6 * t_dense / sweeps,
             "dense_TFLOPs_fp64": flops / t_dense / 1e12,
-            "fp64_peak_note": "B200 FP64: 33.6 TFLOP/s measured with DFMA (scripts/ubench.cu), 40 nominal (vector and tensor)",
+            "fp64_peak_note": "B200 FP64: 33.6 TFLOP/s measured with DFMA (scripts/ubench.cu), 40 nominal (vector and tensor); the "
+                              "whole-loop figure includes the epilogue launches and runs at the sustained (power-capped) clock",
+            "tensor_pipe_cycles_active_pct_ncu": ncu.get("tensor_pipe_cycles_active_pct"),
+            "gemm_TFLOPs_in_ncu_capture": ncu.get("TFLOPs_in_capture"), "ncu_source": ncu.get("source"),
             "ell_gather_seconds_for_%d_candidates" % B_gather: t_gather,
             "ns_per_candidate_sweep": {"dense": 1e9 * per_cs_dense, "ell_gather": 1e9 * per_cs_gather},
             "speedup_over_ell_gather": per_cs_gather / per_cs_dense}
