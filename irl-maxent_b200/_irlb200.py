@@ -421,6 +421,10 @@ launch_log = None
 n_launches = 0          # launches of this library's kernels since import (bench.py: gpu_launches)
 
 
+# NVTX ranges around every entry point (tracing), visible in nsys / ncu --nvtx; IRLB200_NVTX=0 disables
+_NVTX = os.environ.get("IRLB200_NVTX", "1") != "0"
+
+
 class _timed:
     def __init__(self, name, launches=1):
         self.name, self.launches = name, launches
@@ -428,6 +432,8 @@ class _timed:
     def __enter__(self):
         global n_launches
         n_launches += self.launches
+        if _NVTX:
+            _torch().cuda.nvtx.range_push("irlb200:" + self.name)     # one range per fixed point / launch group
         if launch_log is not None:
             torch = _torch()
             self.t0 = torch.cuda.Event(enable_timing=True)
@@ -439,6 +445,8 @@ class _timed:
         if launch_log is not None:
             self.t1.record()
             launch_log.append((self.name, self.t0, self.t1))
+        if _NVTX:
+            _torch().cuda.nvtx.range_pop()
         return False
 
 

@@ -556,7 +556,9 @@ static int pick_mode(int mode, int B, int S, int A, bool fused, int *out) {
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const bool fits_cta = cta_smem_bytes(S, A, fused) <= (size_t)optin;
     if (mode == IRLB200_MODE_AUTO) mode = (fits_cta && (B > 1 || S <= 2048)) ? IRLB200_MODE_CTA : IRLB200_MODE_GRID;
-    if (mode == IRLB200_MODE_CLUSTER) return fail(IRLB200_ELIMIT, "cluster mode is not available in this build");
+    if (mode == IRLB200_MODE_CLUSTER)
+        return fail(IRLB200_ELIMIT, "thread-block-cluster kernels exist for irlb200_backward and irlb200_svf on grid-stencil "
+                                    "tables (n <= 128, n % 4 == 0); this operator / table runs in CTA or cooperative-grid mode");
     if (mode == IRLB200_MODE_CTA && !fits_cta) return fail(IRLB200_ELIMIT, "problem does not fit one CTA's shared memory");
     if (mode == IRLB200_MODE_GRID && B != 1) return fail(IRLB200_ELIMIT, "grid mode takes one problem per call");
     if (mode != IRLB200_MODE_CTA && mode != IRLB200_MODE_GRID) return fail(IRLB200_EINVAL, "unknown mode");
