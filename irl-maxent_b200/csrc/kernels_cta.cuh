@@ -262,6 +262,166 @@ struct IrlLoopArgs {
     int32_t *last_counts;        // [B][2] or null: sweeps of the last gradient step
 };
 
+// ---------------------------------------------------------------------------
+// Soft value iteration of ONE tiny world by FOUR warps (lane = state, warp = action), for the latency-bound
+// case of a single causal problem (BASELINE configs[1]): one warp runs a sweep as ~300 dependent instructions
+// (4 exp + 1 log per state, ncu: 54 % stall_wait, 1 240 cycles per sweep).  Here warp a computes only
+// q_a = r + g P_a.v and exp(q_a - m); the four warps exchange q and the exponentials through shared memory (two
+// bar.sync per sweep, buffers alternate by sweep parity) and every warp then forms the same v' = m + log(sum) --
+// so each warp keeps its own full copy of v in registers, gathers by shuffle, and votes for itself.
+// The expression tree per state is exactly succ_update<kOpSoftVI>: bitwise the one-warp kernel's results.
+// ---------------------------------------------------------------------------
+struct Cta4Smem {
+    double q[2][4][32];
+    double e[2][5][32];          // [..][4] = exp(phi - m)
+    double pol[4][32];
+};
+
+__device__ __forceinline__ void cta4_soft_vi(const WarpWorld &wd, const StepBatch &bt, Cta4Smem &sm, const double r,
+                                             const int lane, const int wa, double (&pol)[4], int &n_pol, int &st_pol) {
+    constexpr int A = 4, K = 5;
+    constexpr unsigned FULL = 0xffffffffu;
+    const SuccArgs &s = bt.s;
+    const bool act = wd.act;
+    double x = kNegHuge;                                                         // maxent.py:323
+    double q[A], qa = 0.0;
+    double pra[K];                                                               // this warp's action row, in registers
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        pra[j] = wd.pr[0][j];
+#pragma unroll
+        for (int a = 1; a < A; ++a) pra[j] = (a == wa) ? wd.pr[a][j] : pra[j];
+    }
+    n_pol = 0;
+    st_pol = IRLB200_ST_CONVERGED;
+    const int limit = s.max_sweeps > 0 ? s.max_sweeps : 0x7fffffff;
+    for (;;) {
+        const int par = n_pol & 1;
+        double dot = 0.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) dot = fma(pra[j], __shfl_sync(FULL, x, wd.ix[j]), dot);
+        qa = r + s.discount * dot;                                                // :329, this warp's action
+        sm.q[par][wa][lane] = qa;
+        __syncthreads();
+#pragma unroll
+        for (int a = 0; a < A; ++a) q[a] = sm.q[par][a][lane];
+        double m = wd.c1;
+#pragma unroll
+        for (int a = 0; a < A; ++a) m = max_nan(m, q[a]);
+        double xn;
+        const bool finite = fabs(m) < INFINITY;
+        // the branch may differ between lanes, never between the warps of one lane: every warp sees the same m
+        if (finite) {
+            sm.e[par][wa][lane] = exp(qa - m);
+            if (wa == 0) sm.e[par][4][lane] = (wd.c1 != -INFINITY) ? exp(wd.c1 - m) : 0.0;
+        }
+        __syncthreads();
+        if (finite) {
+            double ssum = sm.e[par][4][lane];
+#pragma unroll
+            for (int a = 0; a < A; ++a) ssum += sm.e[par][a][lane];
+            xn = m + log(ssum);
+        } else {
+            xn = wd.c1;                                                          // the reference's fold, verbatim
+#pragma unroll 1
+            for (int a = 0; a < A; ++a) xn = softmax2(xn, q[a]);
+        }
+        const double diff = fabs(xn - x);
+        x = xn;
+        ++n_pol;
+        const bool nan = __any_sync(FULL, act && diff != diff);
+        const bool gt = __any_sync(FULL, act && diff > s.eps);
+        if (nan) { st_pol = IRLB200_ST_NONFINITE; break; }
+        if (!gt) break;
+        if (n_pol >= limit) { st_pol = IRLB200_ST_MAXSWEEPS; break; }
+    }
+    // policy of the last sweep (:341): q of that sweep against the new v; one action per warp, then shared
+    sm.pol[wa][lane] = exp(qa - x);
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < A; ++a) pol[a] = sm.pol[a][lane];
+    __syncthreads();                                                             // sm.pol is rewritten next step
+}
+
+// forward pass of a warp's world from a given policy (the second half of warp_world_step)
+__device__ __forceinline__ double warp_world_forward(const WarpWorld &wd, const StepBatch &bt, const double (&pol)[4],
+                                                     int &n_svf, int &st_svf) {
+    constexpr int A = 4, K = 5;
+    constexpr unsigned FULL = 0xffffffffu;
+    const SvfArgs &f = bt.f;
+    const bool act = wd.act;
+    double w[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        double acc = 0.0;
+#pragma unroll
+        for (int a = 0; a < A; ++a) acc = fma(wd.pp[a][j], __shfl_sync(FULL, pol[a], wd.px[j]), acc);
+        const int pterm = __shfl_sync(FULL, wd.is_term, wd.px[j]);
+        w[j] = (pterm || !act) ? 0.0 : acc;
+    }
+    double d = 0.0;
+    n_svf = 0;
+    st_svf = IRLB200_ST_CONVERGED;
+    const int limit = f.max_sweeps > 0 ? f.max_sweeps : 0x7fffffff;
+    for (;;) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc = fma(w[j], __shfl_sync(FULL, d, wd.px[j]), acc);
+        const double dn = wd.p0 + acc;
+        const double diff = fabs(dn - d);
+        d = dn;
+        ++n_svf;
+        const bool nan = __any_sync(FULL, act && diff != diff);
+        const bool gt = __any_sync(FULL, act && diff > f.eps);
+        if (nan) { st_svf = IRLB200_ST_NONFINITE; break; }
+        if (!gt) break;
+        if (n_svf >= limit) { st_svf = IRLB200_ST_MAXSWEEPS; break; }
+    }
+    return d;
+}
+
+// irl_causal's outer loop, one CTA of four warps per problem (see cta4_soft_vi); the forward pass and the
+// optimizer step are computed by every warp redundantly (identical registers, no exchange), warp 0 writes.
+__global__ void __launch_bounds__(128) irl_cta4_kernel(const StepBatch bt, const IrlLoopArgs lp, const int B) {
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ Cta4Smem sm;
+    const int lane = threadIdx.x & 31, wa = threadIdx.x >> 5;
+    const size_t b = blockIdx.x;
+    if (b >= (size_t)B || lp.done[b]) return;                                    // uniform over the CTA
+    const int S = bt.s.S;
+    WarpWorld wd;
+    warp_world_load<true>(wd, bt, b, lane);
+    const int me = wd.act ? lane : 0;
+    const double ef = wd.act ? bt.f.e_features[b * bt.ef_stride + me] : 0.0;
+    const double *lr = lp.lr + b * lp.lr_stride;
+    double theta = wd.act ? lp.theta[b * S + me] : 0.0;
+    int steps = 0, done = 0, n_pol = 0, n_svf = 0;
+    for (int k = 0; k < lp.n_rates; ++k) {
+        double pol[4];
+        int st_pol, st_svf;
+        cta4_soft_vi(wd, bt, sm, theta, lane, wa, pol, n_pol, st_pol);
+        const double d = warp_world_forward(wd, bt, pol, n_svf, st_svf);
+        const double grad = ef - d;
+        const double rate = __ldg(lr + k);
+        const double old = theta;
+        if (lp.kind == 0) theta = __dadd_rn(theta, __dmul_rn(rate, grad));
+        else theta = __dmul_rn(theta, exp(__dmul_rn(rate, grad)));
+        ++steps;
+        const double diff = fabs(old - theta);
+        const bool nan = __any_sync(FULL, wd.act && diff != diff);
+        const bool gt = __any_sync(FULL, wd.act && diff > lp.eps);
+        if (nan || !gt) { done = 1; break; }
+    }
+    if (wa == 0) {
+        if (wd.act) lp.theta[b * S + me] = theta;
+        if (lane == 0) {
+            lp.steps[b] += steps;
+            lp.done[b] = done;
+            if (lp.last_counts) { lp.last_counts[2 * b] = n_pol; lp.last_counts[2 * b + 1] = n_svf; }
+        }
+    }
+}
+
 template <bool CAUSAL>
 __global__ void __launch_bounds__(128) irl_warp_kernel(const StepBatch bt, const IrlLoopArgs lp, const int B) {
     constexpr unsigned FULL = 0xffffffffu;

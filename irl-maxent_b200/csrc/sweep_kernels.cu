@@ -781,7 +781,9 @@ extern "C" int irlb200_irl_small(const irlb200_tables *t, int B, int causal, dou
     lp.theta = theta; lp.lr = lr; lp.lr_stride = lr_shared ? 0 : (size_t)n_rates; lp.n_rates = n_rates;
     lp.kind = opt_kind; lp.eps = eps; lp.steps = steps; lp.done = done; lp.last_counts = last_counts;
     cudaStream_t st = (cudaStream_t)stream;
-    if (causal) irl_warp_kernel<true><<<(B + 3) / 4, 128, 0, st>>>(bt, lp, B);
+    // few causal problems: latency bound -> four warps per problem (one per action); batches: one warp each
+    if (causal && B <= env_int("IRLB200_CTA4_MAX_BATCH", 64)) irl_cta4_kernel<<<B, 128, 0, st>>>(bt, lp, B);
+    else if (causal) irl_warp_kernel<true><<<(B + 3) / 4, 128, 0, st>>>(bt, lp, B);
     else irl_warp_kernel<false><<<(B + 3) / 4, 128, 0, st>>>(bt, lp, B);
     LAUNCH_CHECK("irl_warp_kernel");
     return IRLB200_OK;
