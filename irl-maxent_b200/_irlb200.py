@@ -768,7 +768,8 @@ def irl_small(tables, theta, e_features, p_initial, terminal_mask_t, opt_kind, r
 # ---------------------------------------------------------------------------
 
 class DenseTables:
-    """A dense p_transition[S, S', A] packed for the FP64 tensor-core contraction (irlb200_dense_pack)."""
+    """A dense p_transition[S, S', A] packed for the FP64 tensor-core contraction (irlb200_dense_pack).
+    The handle owns one work buffer, reused by its calls: use a handle from one stream at a time."""
 
     def __init__(self, p_transition):
         torch = require_cuda()

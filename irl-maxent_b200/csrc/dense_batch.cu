@@ -164,11 +164,9 @@ __global__ void __launch_bounds__(32 * WM * WN, (WM * WN <= 4) ? 4 : 1)
 template <int WM, int WN>
 static int launch_gemm_cfg(const double *Am, const double *Xt, double *Ct, int M, int N, int K, cudaStream_t st) {
     using Cfg = GemmCfg<WM, WN>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (Cfg::SMEM > 48 * 1024) {          // per device and context: set on every call (cheap), like the other launchers
         cudaError_t e = cudaFuncSetAttribute(dense_gemm_kernel<WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
         if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(dense gemm)");
-        attr_set = true;
     }
     dim3 grid((M + Cfg::TM - 1) / Cfg::TM, (N + Cfg::TN - 1) / Cfg::TN);
     dense_gemm_kernel<WM, WN><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(Am, Xt, Ct, M, N, K);
