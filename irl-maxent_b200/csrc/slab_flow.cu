@@ -65,7 +65,9 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned 
 template <int OP, int A_T, int K_T, int U, int MINB>
 __global__ void __launch_bounds__(256, MINB)
     slab_flow_kernel(const OverlapArgs a, const SlabPeers pe, unsigned char *base, unsigned long long *progress,
-                     double *snap, const int chunk, const int edge, int32_t *n_iter, int32_t *status) {
+                     double *snap, const int chunk, const int edge, const int res_cap, int32_t *n_iter,
+                     int32_t *status) {
+    extern __shared__ __align__(16) unsigned char res_raw[];   // forward pass: table rows of the CTA's first states
     __shared__ unsigned long long s_gt, s_nanmask;
     __shared__ int s_nan, s_dead;
     constexpr int QN = A_T > 0 ? A_T : kMaxDynA;
@@ -105,6 +107,16 @@ __global__ void __launch_bounds__(256, MINB)
     const int d_lo = cta_of(max(beg - h, 0)), d_hi = cta_of(min(end + h, cnt) - 1);
     // within one grid row of the neighbouring slab: reads its boundary row from the mailbox
     const bool near_lo = has_lo && beg < h, near_hi = has_hi && end > cnt - h;
+    // Forward pass: a CTA's range is FIXED, so the rows of its first `nres` states (predecessor indices, merged
+    // weights, p_initial: 4 K + 8 K + 8 bytes per state) are copied into shared memory once and every sweep reads
+    // them from there -- at 8 GPUs a 2048 x 2048 slab is ~900 states per CTA and fits entirely (198 kB per SM),
+    // leaving only the iterate on the L2 path.  The launcher asks for it only when EVERY CTA's range fits
+    // (res_cap >= the longest range); otherwise res_cap = 0 and all rows are streamed.
+    constexpr int KR = K_T > 0 ? K_T : 1;
+    const int nres = (OP == 3 && K_T > 0) ? min(end - beg, res_cap) : 0;
+    int *s_idx = reinterpret_cast<int *>(res_raw);                                            // [K][nres]
+    double *s_w = reinterpret_cast<double *>(res_raw + (((size_t)KR * nres * 4 + 15) & ~(size_t)15));   // [K][nres]
+    double *s_p0 = s_w + (size_t)KR * nres;                                                   // [nres]
 
     unsigned seq = 0;                  // full-barrier sequence number
     bool dead = false;
@@ -237,8 +249,14 @@ __global__ void __launch_bounds__(256, MINB)
                 double acc = 0.0;
                 for (int aa = 0; aa < A; ++aa)
                     acc = fma(__ldg(a.p + ((size_t)aa * K + j) * cnt + i), a.policy_in[(size_t)pred * A + aa], acc);
-                a.w[(size_t)j * cnt + i] = a.term[pred] ? 0.0 : acc;
+                const double wj = a.term[pred] ? 0.0 : acc;
+                a.w[(size_t)j * cnt + i] = wj;
+                if (i - beg < nres) {
+                    s_idx[j * nres + (i - beg)] = pred;
+                    s_w[j * nres + (i - beg)] = wj;
+                }
             }
+            if (i - beg < nres) s_p0[i - beg] = a.c0[i];
         }
         put(0u, i, OP == kOpSoftVI ? kNegHuge : 0.0);
     }
@@ -255,7 +273,7 @@ __global__ void __launch_bounds__(256, MINB)
         const double *x_in = (q & 1u) ? buf1 : buf0;
         bool gt = false, nan = false;
         auto body = [&](auto xl) {
-            if (OP == 3 && K_T > 0 && U > 1) {
+            if (OP == 3 && K_T > 0) {
                 constexpr int KK = K_T > 0 ? K_T : 1, UU = U > 0 ? U : 1;
                 for (int i0 = beg + tid; i0 < end; i0 += UU * nthr) {
                     int ix[UU][KK];
@@ -263,12 +281,22 @@ __global__ void __launch_bounds__(256, MINB)
 #pragma unroll
                     for (int u = 0; u < UU; ++u) {
                         const int i = min(i0 + u * nthr, end - 1);      // clamped: inactive slots repeat a valid state
+                        const int li = i - beg;
+                        if (li < nres) {                                // resident rows (shared memory)
 #pragma unroll
-                        for (int j = 0; j < KK; ++j) {
-                            ix[u][j] = __ldg(a.idx + (size_t)j * cnt + i);
-                            wv[u][j] = __ldg(a.w + (size_t)j * cnt + i);
+                            for (int j = 0; j < KK; ++j) {
+                                ix[u][j] = s_idx[j * nres + li];
+                                wv[u][j] = s_w[j * nres + li];
+                            }
+                            p0v[u] = s_p0[li];
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < KK; ++j) {
+                                ix[u][j] = __ldg(a.idx + (size_t)j * cnt + i);
+                                wv[u][j] = __ldg(a.w + (size_t)j * cnt + i);
+                            }
+                            p0v[u] = __ldg(a.c0 + i);
                         }
-                        p0v[u] = __ldg(a.c0 + i);
                         xo[u] = ld_cg(x_in + lo + i);
                     }
                     // Only the thread that OWNS a state may read its neighbours: a mailbox slot is overwritten as
@@ -467,35 +495,76 @@ extern "C" int irlb200_slab_flow(int op, int rank, int world, void *const *block
     }
 
     const int threads = 256;
-    int dev = 0, sms = 0, per_sm = 0;
+    int dev = 0, sms = 0, per_sm = 0, nb = 0, edge = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, 0);
-    if (e != cudaSuccess) return fail_cuda(e, "occupancy(slab flow)");
-    if (per_sm < 1) return fail(IRLB200_ELIMIT, "slab flow kernel does not fit on an SM");
-    if (per_sm > 8) per_sm = 8;
-    const int per_sm_env = flow_env_int("IRLB200_FLOW_CTAS_PER_SM", 0);
-    if (per_sm_env > 0 && per_sm_env < per_sm) per_sm = per_sm_env;
-    long long want = ((long long)cnt + threads - 1) / threads, cap = (long long)sms * per_sm;
-    int nb = (int)(want < cap ? want : cap);
-    const int nb_env = flow_env_int("IRLB200_FLOW_BLOCKS", 0);
-    if (nb_env > 0 && nb_env < nb) nb = nb_env;
-    if (nb < 1) nb = 1;
     if (chunk <= 0) chunk = flow_env_int("IRLB200_FLOW_CHUNK", 32);
     if (chunk > 64) chunk = 64;
-    // CTAs per boundary row (see the kernel): about one state per thread, at most 8
-    int edge = halo / threads;
-    edge = edge < 1 ? 1 : (edge > 8 ? 8 : edge);
-    edge = flow_env_int("IRLB200_FLOW_EDGE_CTAS", edge);
-    if (world == 1 || edge < 0 || cnt < 4 * halo || nb < 8 * edge || halo < edge) edge = 0;
+    cudaError_t e = cudaSuccess;
+    // grid of a kernel variant: all CTAs co-resident (cooperative launch), one CTA per >= 256 states
+    auto plan = [&](const void *kern) -> int {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0);
+        if (e != cudaSuccess) return fail_cuda(e, "occupancy(slab flow)");
+        if (per_sm < 1) return fail(IRLB200_ELIMIT, "slab flow kernel does not fit on an SM");
+        if (per_sm > 8) per_sm = 8;
+        const int per_sm_env = flow_env_int("IRLB200_FLOW_CTAS_PER_SM", 0);
+        if (per_sm_env > 0 && per_sm_env < per_sm) per_sm = per_sm_env;
+        long long want = ((long long)cnt + threads - 1) / threads, cap = (long long)sms * per_sm;
+        nb = (int)(want < cap ? want : cap);
+        const int nb_env = flow_env_int("IRLB200_FLOW_BLOCKS", 0);
+        if (nb_env > 0 && nb_env < nb) nb = nb_env;
+        if (nb < 1) nb = 1;
+        // CTAs per boundary row (see the kernel): about one state per thread, at most 8
+        edge = halo / threads;
+        edge = edge < 1 ? 1 : (edge > 8 ? 8 : edge);
+        edge = flow_env_int("IRLB200_FLOW_EDGE_CTAS", edge);
+        if (world == 1 || edge < 0 || cnt < 4 * halo || nb < 8 * edge || halo < edge) edge = 0;
+        return IRLB200_OK;
+    };
+
+    // Forward pass with compile-time K: if the table rows of EVERY CTA's range fit its share of the SM's shared
+    // memory, keep them there for the whole fixed point (2048 x 2048 on 8 GPUs: 903 states x 56 B per CTA,
+    // 4 CTAs per SM; measured 4.77 -> 4.23 us per sweep on that slab).  Partial residency was measured and
+    // dropped: the large carve-out shrinks L1 and the streamed rest gets slower (23.9 -> 28.5 us at 2 M states).
+    size_t dyn = 0;
+    int res_cap = 0;
+    if (op == 3 && (fast || compact) && flow_env_int("IRLB200_FLOW_RESIDENT", 1) && fwd == 24) {
+        const void *k1 = fast ? (const void *)slab_flow_kernel<3, 4, 5, 1, 4> : (const void *)slab_flow_kernel<3, 4, 4, 1, 4>;
+        if (int rc = plan(k1)) return rc;
+        const int n_edge = (rank > 0 ? edge : 0) + (rank < world - 1 ? edge : 0);
+        const long long len_max = edge ? ((long long)cnt - (long long)halo * ((rank > 0) + (rank < world - 1))) / (nb - n_edge) + 2
+                                       : ((long long)cnt + nb - 1) / nb + 1;
+        int smem_sm = 0, smem_optin = 0, reserved = 1024;
+        cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, dev);
+        long long share = (long long)smem_sm / per_sm - reserved - 256;           // 256: the kernel's static shared memory
+        if (share > smem_optin) share = smem_optin;
+        share &= ~127ll;
+        const long long need = len_max * (12 * K + 8) + 32;
+        const long long rows_halo = edge ? ((long long)halo + edge - 1) / edge + 1 : 0;   // an edge CTA's range
+        if (share >= need && share >= rows_halo * (12 * K + 8) + 32) {
+            int fit = 0;
+            e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)share);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, k1, threads, (size_t)share);
+            if (e == cudaSuccess && fit >= per_sm) {
+                k = k1;
+                dyn = (size_t)share;
+                res_cap = (int)((dyn - 16) / (size_t)(12 * K + 8));
+            }
+            cudaGetLastError();
+        }
+    }
+    if (!dyn)
+        if (int rc = plan(k)) return rc;
 
     unsigned long long *progress = static_cast<unsigned long long *>(work);
     const size_t prog_bytes = (size_t)sms * 8 * kProgressStride * sizeof(unsigned long long);
     double *snap = reinterpret_cast<double *>(static_cast<unsigned char *>(work) + ((prog_bytes + 255) & ~(size_t)255));
     e = cudaMemsetAsync(progress, 0, prog_bytes, st);
     if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync(slab flow progress)");
-    void *params[9] = {&oa, &pe, &base, &progress, &snap, &chunk, &edge, &n_iter, &status};
-    e = cudaLaunchCooperativeKernel(k, dim3(nb), dim3(threads), params, 0, st);
+    void *params[10] = {&oa, &pe, &base, &progress, &snap, &chunk, &edge, &res_cap, &n_iter, &status};
+    e = cudaLaunchCooperativeKernel(k, dim3(nb), dim3(threads), params, dyn, st);
     if (e != cudaSuccess) return fail_cuda(e, "cudaLaunchCooperativeKernel(slab flow)");
     return IRLB200_OK;
 }
