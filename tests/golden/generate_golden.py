@@ -284,6 +284,17 @@ def gen_optimizer():
     print("optimizer.npz", len(out))
 
 
+def gen_main_fixture():
+    """The reference's driver, byte for byte (the caller that must run unchanged on the engine; run by
+    tests/test_gpu_parity.py::test_the_reference_main_py_runs_unchanged_on_the_gpu), and its licence."""
+    import hashlib
+    import shutil
+    shutil.copyfile(os.path.join(REF, "main.py"), os.path.join(OUT, "reference_main_py.fixture"))
+    shutil.copyfile(os.path.join(os.path.dirname(REF), "LICENSE"), os.path.join(OUT, "reference_main_py.LICENSE"))
+    print("reference_main_py.fixture sha256",
+          hashlib.sha256(open(os.path.join(OUT, "reference_main_py.fixture"), "rb").read()).hexdigest())
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("reference not present at %s: fixtures can only be regenerated in the build container" % REF)
@@ -292,3 +303,4 @@ if __name__ == "__main__":
     gen_random()
     gen_optimizer()
     gen_e2e()
+    gen_main_fixture()

@@ -331,3 +331,40 @@ def test_table_cache_fingerprint_sees_in_place_edits():
     assert E._fingerprint(t) != f0
     import maxent as M
     assert M.invalidate is E.invalidate and M.clear_cache is E.clear_cache
+
+
+def test_device_loop_is_taken_only_for_untouched_builtin_optimizers():
+    """The device-side outer loop (irlb200_irl_small) knows the update rule of plain `Sga` / `ExpSga` only: a
+    wrapper, a subclass, `normalize=True`, NormalizeGrad or a patched `step` must keep the generic host loop."""
+    import maxent as M
+    assert M._builtin_optimizer_kind(O.Sga(lr=0.1)) == 0
+    assert M._builtin_optimizer_kind(O.ExpSga(lr=O.linear_decay(0.2))) == 1
+    assert M._builtin_optimizer_kind(O.ExpSga(lr=0.1, normalize=True)) is None
+    assert M._builtin_optimizer_kind(O.Sga(lr=0.1).normalize_grad()) is None
+
+    class Mine(O.ExpSga):
+        pass
+
+    class Wrapped:
+        def __init__(self, inner):
+            self.inner = inner
+
+        def reset(self, p):
+            self.inner.reset(p)
+
+        def step(self, g):
+            self.inner.step(g)
+
+    assert M._builtin_optimizer_kind(Mine(lr=0.1)) is None
+    assert M._builtin_optimizer_kind(Wrapped(O.ExpSga(lr=0.1))) is None
+    orig = O.ExpSga.step
+    try:
+        O.ExpSga.step = lambda self, grad, *a, **k: orig(self, grad, *a, **k)
+        assert M._builtin_optimizer_kind(O.ExpSga(lr=0.1)) is None
+    finally:
+        O.ExpSga.step = orig
+    assert M._builtin_optimizer_kind(O.ExpSga(lr=0.1)) == 1
+    # the learning rates handed to the kernel are the schedule's own values, step counter untouched
+    opt = O.ExpSga(lr=O.linear_decay(lr0=0.2))
+    opt.reset(np.ones(3))
+    assert [O._rate(opt.lr, opt.k + i) for i in range(3)] == [0.2, 0.1, 0.2 / 3] and opt.k == 0
