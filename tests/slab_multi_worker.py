@@ -59,6 +59,31 @@ def main():
             print("slab parity ok: n=%d ranks=%d flow=%s soft-VI %d forward %d (status %d) VI %d sweeps"
                   % (n, world, flow, n_lap, n_fw, st_fw, n_vi), flush=True)
         g.close()
+    # C5 at FULL size (2048 x 2048, 4.2 M states): the N-rank dataflow kernel must be bitwise the 1-GPU
+    # cooperative-grid kernel, which tests/test_gpu_parity.py::test_c5_full_size_sweeps_against_sparse_oracle
+    # holds to 1e-10 of the oracle at this size (fixed budgets: convergence takes 10^3 / 10^7 sweeps)
+    n = 2048
+    S = n * n
+    g = slab.PeerSlabGrid(n, 0.2, flow=True)
+    rng = np.random.default_rng(5)
+    r = -0.1 + 0.05 * rng.standard_normal(S); r[S - 1] = 1.0
+    phi = np.full(S, -np.inf); phi[S - 1] = 0.0
+    p0 = np.zeros(S); p0[0] = 0.5; p0[S // 2 + n // 2] = 0.5
+    k = 40
+    pol, v = g.soft_vi(g.local(r), g.local(phi), 0.9, 1e-5, max_sweeps=k)
+    assert g.last_n_iter == k and g.last_status == slab.ST_MAXSWEEPS
+    uniform = torch.full((g.cnt, 4), 0.25, dtype=torch.float64, device="cuda")
+    d = g.svf(g.local(p0), [S - 1], uniform, 1e-5, max_sweeps=k)
+    assert g.last_n_iter == k
+    t1 = E.gridworld_tables(n, 0.2, slots=4)
+    _, v1 = E.soft_vi(t1, E.terminal_phi([S - 1], S), r, 0.9, max_sweeps=k, mode=E.MODE_GRID, want_value=True)
+    d1 = E.svf(t1, p0, E.terminal_mask([S - 1], S), torch.full((S, 4), 0.25, dtype=torch.float64, device="cuda"),
+               1e-5, max_sweeps=k, mode=E.MODE_GRID)
+    assert bool((v == v1[0, g.lo:g.hi]).all()) and bool((d == d1[0, g.lo:g.hi]).all()), "C5 full size: slab != 1-GPU kernel"
+    g.close()
+    if rank == 0:
+        print("slab parity ok: 2048x2048 over %d ranks, %d sweeps of soft-VI and of the forward pass bitwise the 1-GPU kernel"
+              % (world, k), flush=True)
     dist.barrier()
     if rank == 0:
         print("SLAB_MULTI_OK", flush=True)
