@@ -241,6 +241,92 @@ def test_guards_and_status(golden):
     assert counts()[0] <= n_ref + 16
 
 
+@pytest.mark.parametrize("n", [8, 32])
+def test_nan_exit_sweep_against_the_oracle(n, monkeypatch):
+    """`while delta > eps` ends on NaN (maxent.py:108).  Against the sparse restatement's NaN-exit sweep: the
+    generic kernels (template, streamed, cooperative grid) and the slab kernels stop on exactly that sweep; the
+    hand-tuned tiled / fast forward kernels look for a non-finite iterate every 16 sweeps and therefore stop on
+    the next multiple of 16 -- never earlier, at most 15 sweeps later (documented in DESIGN.md section 2)."""
+    from oracle import c_port as C
+    S = n * n
+    sidx, sp = C.ell_from_sparse(SP.icy_gridworld_sparse(n, 0.2))
+    r = np.full(S, -0.1); r[S - 1] = 1.0
+    phi = np.full(S, -np.inf); phi[S - 1] = 0.0
+    pol, _, _ = C.soft_vi(sidx, sp, phi, r, 0.9)
+    p0 = np.zeros(S); p0[0] = 1.0
+    far = S - 2                                  # poison a state the start mass needs several sweeps to reach
+    pol[far, 2] = np.nan
+    _, n_ref = C.svf(sidx, sp, p0, [S - 1], pol, 1e-5)
+    assert n_ref >= 1
+    t = E.gridworld_tables(n, 0.2)
+    mask = E.terminal_mask([S - 1], S)
+    E.svf(t, p0, mask, pol, 1e-5)                                        # tiled kernel
+    n_tiled, st = int(counts()[0]), int(E.last_info.stati()[0])
+    assert st == E.ST_NONFINITE and n_ref <= n_tiled <= n_ref + 15 and n_tiled % 16 == 0
+    monkeypatch.setenv("IRLB200_SVF_TILE", "0")
+    monkeypatch.setenv("IRLB200_FORCE_STREAMED", "1")                    # generic template kernel
+    E.svf(t, p0, mask, pol, 1e-5)
+    assert int(counts()[0]) == n_ref and int(E.last_info.stati()[0]) == E.ST_NONFINITE
+    E.svf(t, p0, mask, pol, 1e-5, mode=E.MODE_GRID)                      # cooperative grid
+    assert int(counts()[0]) == n_ref and int(E.last_info.stati()[0]) == E.ST_NONFINITE
+    import slab
+    g = slab.PeerSlabGrid(n, 0.2, flow=True, chunk_sweeps=5)             # dataflow slab kernel: exact, via replay
+    try:
+        g.svf(p0, [S - 1], pol, 1e-5)
+        assert (g.last_n_iter, g.last_status) == (n_ref, E.ST_NONFINITE)
+    finally:
+        g.close()
+
+
+@pytest.mark.timeout(120)
+def test_slab_flow_kernel_aborts_instead_of_hanging_when_a_peer_is_missing():
+    """Failure detection of the multi-GPU dataflow kernel, on ONE GPU: rank 0 of a world of two is
+    launched while "rank 1" (a second local block standing in for the peer's memory) never runs.  The CTAs of the
+    boundary row wait for mailbox values that never arrive; after `timeout_s` they raise the abort word, every
+    spin loop sees it, all CTAs meet at the chunk barrier and the launch returns IRLB200_ST_ABORTED -- no hang."""
+    import ctypes
+    import time
+    import torch
+    n = 64
+    S, half = n * n, n * n // 2
+    lib = E.load_library()
+    E.require_cuda()
+    dev = E._dev()
+    blocks = []
+    try:
+        for _ in range(2):
+            p = ctypes.c_void_p()
+            E._check(lib.irlb200_peer_alloc(lib.irlb200_slab_flow_block_bytes(S, n), ctypes.byref(p)))
+            E._check(lib.irlb200_slab_flow_reset(p, S, n, E._stream()))
+            blocks.append(p)
+        arr = (ctypes.c_void_p * 2)(blocks[0].value, blocks[1].value)
+        K, A = 4, 4
+        t = dict(idx=torch.empty((K, half), dtype=torch.int32, device=dev),
+                 p=torch.empty((A, K, half), dtype=torch.float64, device=dev),
+                 pidx=torch.empty((K, half), dtype=torch.int32, device=dev),
+                 pp=torch.empty((A, K, half), dtype=torch.float64, device=dev))
+        E._check(lib.irlb200_gridworld_tables_range_k(n, 1, 0.2, 0, half, K, E._ptr(t["idx"]), E._ptr(t["p"]),
+                                                      E._ptr(t["pidx"]), E._ptr(t["pp"]), E._stream()))
+        r = torch.full((half,), -0.1, dtype=torch.float64, device=dev)
+        out = torch.empty(half, dtype=torch.float64, device=dev)
+        n_iter = torch.zeros(1, dtype=torch.int32, device=dev)
+        status = torch.full((1,), -7, dtype=torch.int32, device=dev)
+        work = torch.empty(int(lib.irlb200_slab_flow_work_bytes(half)), dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        E._check(lib.irlb200_slab_flow(2, 0, 2, arr, S, 0, half, n, A, K, E._ptr(t["idx"]), E._ptr(t["p"]), E._ptr(r),
+                                       None, None, None, None, 0.9, 1e-4, 100000, 0, E._ptr(out), None, E._ptr(n_iter),
+                                       E._ptr(status), 0.5, 0, E._ptr(work), work.numel(), E._stream()))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert int(status.item()) == E.ST_ABORTED, (int(status.item()), int(n_iter.item()))
+        assert 0.4 < dt < 10.0, dt
+    finally:
+        torch.cuda.synchronize()
+        for p in blocks:
+            lib.irlb200_peer_free(p)
+
+
 # ------------------------------------------------------------- public API ---
 
 def test_module_api_numpy_roundtrip(golden):
