@@ -441,6 +441,9 @@ def dense_batch_line(S=1024, A=4, B=4096, sweeps=24, B_gather=256):
         return a.elapsed_time(b) / 1e3
 
     t_dense = timed(lambda: E.dense_soft_vi(dt, phi, rewards, 0.9, 1e-30, max_sweeps=sweeps))
+    # yardstick: the library DGEMM of the same shape (no epilogue, no stop rule), sustained over as many calls
+    Pa, X = dt.packed[:A * S * S].view(A * S, S), rewards.t().contiguous()
+    t_blas = timed(lambda: [torch.matmul(Pa, X) for _ in range(sweeps)])
     tabs = E.compress_dense(P)
     t_gather = timed(lambda: E.soft_vi(tabs, phi, rewards[:B_gather], 0.9, 1e-30, max_sweeps=sweeps))
     flops = 2.0 * A * S * S * B * sweeps
@@ -451,6 +454,8 @@ def dense_batch_line(S=1024, A=4, B=4096, sweeps=24, B_gather=256):
             "dense_TFLOPs_fp64": flops / t_dense / 1e12,
             "fp64_peak_note": "B200 FP64: 33.6 TFLOP/s measured with DFMA (scripts/ubench.cu), 40 nominal (vector and tensor); the "
                               "whole-loop figure includes the epilogue launches and runs at the sustained (power-capped) clock",
+            "cublas_dgemm_same_shape_TFLOPs": flops / t_blas / 1e12,
+            "fraction_of_cublas_dgemm": t_blas / t_dense,
             "tensor_pipe_cycles_active_pct_ncu": ncu.get("tensor_pipe_cycles_active_pct"),
             "gemm_TFLOPs_in_ncu_capture": ncu.get("TFLOPs_in_capture"), "ncu_source": ncu.get("source"),
             "ell_gather_seconds_for_%d_candidates" % B_gather: t_gather,

@@ -62,6 +62,10 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem, bool pre
     const int bytes = pred ? 8 : 0;                                // src-size 0: zero fill
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(saddr), "l"(gmem), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(gmem), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -69,6 +73,17 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, const double a, const double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// the sm_90+ FP64 MMA shape: 16 x 8 x 16, 2 048 FMA per warp instruction (8 x the m8n8k4 of sm_80).  Fragments (CuTe
+// MMA_Traits<SM90_16x8x16_F64F64F64F64_TN>): a_i: row = lane / 4 + 8 (i % 2), k = lane % 4 + 4 (i / 2);
+// b_v: k = lane % 4 + 4 v, n = lane / 4;  c_i: row = lane / 4 + 8 (i / 2), col = 2 (lane % 4) + i % 2.
+__device__ __forceinline__ void dmma_m16n8k16(double (&c)[4], const double (&a)[8], const double (&b)[4]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0, %1, %2, %3}, {%4, %5, %6, %7, %8, %9, %10, %11}, "
+                 "{%12, %13, %14, %15}, {%0, %1, %2, %3};"
+                 : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+                 : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]),
+                   "d"(b[0]), "d"(b[1]), "d"(b[2]), "d"(b[3]));
 }
 
 // CTA tile = (32 WM) x (32 WN), one warp per 32 x 32 sub-tile (4 x 4 MMA tiles, 32 accumulators per thread).
@@ -91,6 +106,18 @@ template <int ROWS, int THREADS>
 __device__ __forceinline__ void load_tile(double *dst, const double *__restrict__ src, int rows, int K, int row0,
                                           int k0, int tid) {
     constexpr int KBS = ROWS * 4 + 4;
+    if ((K & 1) == 0) {
+        // even K: rows start 16-byte aligned, two consecutive k travel as one 16-byte cp.async
+#pragma unroll
+        for (int it = 0; it < (ROWS * kTK / 2) / THREADS; ++it) {
+            const int e = it * THREADS + tid;                      // pair index of the tile, k fastest
+            const int r = e / (kTK / 2), k = (e % (kTK / 2)) * 2;
+            const bool ok = (row0 + r) < rows && (k0 + k) < K;     // K even: the pair is in or out as a whole
+            const double *g = src + (ok ? ((size_t)(row0 + r) * K + k0 + k) : 0);
+            cp_async16(dst + (k >> 2) * KBS + r * 4 + (k & 3), g, ok ? 16 : 0);
+        }
+        return;
+    }
 #pragma unroll
     for (int it = 0; it < (ROWS * kTK) / THREADS; ++it) {
         const int e = it * THREADS + tid;                          // element of the tile, k fastest
@@ -161,6 +188,80 @@ __global__ void __launch_bounds__(32 * WM * WN, (WM * WN <= 4) ? 4 : 1)
     }
 }
 
+// The same tiling with the 16 x 8 x 16 MMA: per k-chunk of 16 a warp issues 2 x 4 MMAs instead of 64.
+template <int WM, int WN>
+__global__ void __launch_bounds__(32 * WM * WN, (WM * WN <= 4) ? 3 : 1)
+    dense_gemm16_kernel(const double *__restrict__ Am, const double *__restrict__ Xt, double *__restrict__ Ct, int M,
+                        int N, int K) {
+    using Cfg = GemmCfg<WM, WN>;
+    extern __shared__ __align__(16) double smem_d[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp / WN, wn = warp % WN;
+    const int m0 = blockIdx.x * Cfg::TM, n0 = blockIdx.y * Cfg::TN;
+    const int nk = (K + kTK - 1) / kTK;
+    double acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[i][j][v] = 0.0;
+    auto stage = [&](int s) { return smem_d + (size_t)s * Cfg::STAGE_DOUBLES; };
+    auto issue = [&](int kc) {
+        if (kc < nk) {
+            double *st = stage(kc % kStages);
+            load_tile<Cfg::TM, Cfg::THREADS>(st, Am, M, K, m0, kc * kTK, tid);
+            load_tile<Cfg::TN, Cfg::THREADS>(st + Cfg::A_DOUBLES, Xt, N, K, n0, kc * kTK, tid);
+        }
+        cp_async_commit();
+    };
+    issue(0);
+    issue(1);
+    for (int kc = 0; kc < nk; ++kc) {
+        issue(kc + 2);
+        cp_async_wait<2>();
+        __syncthreads();
+        const double *As = stage(kc % kStages), *Xs = As + Cfg::A_DOUBLES;
+        double bf[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) bf[j][v] = Xs[v * Cfg::KBS_X + (wn * 32 + j * 8) * 4 + lane];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            double af[8];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) af[v] = As[(v >> 1) * Cfg::KBS_A + (wm * 32 + i * 16 + 8 * (v & 1)) * 4 + lane];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma_m16n8k16(acc[i][j], af, bf[j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const int m = m0 + wm * 32 + i * 16 + (lane >> 2) + 8 * (v >> 1);
+                const int n = n0 + wn * 32 + j * 8 + 2 * (lane & 3) + (v & 1);
+                if (m < M && n < N) Ct[(size_t)n * M + m] = acc[i][j][v];
+            }
+}
+
+template <int WM, int WN>
+static int launch_gemm16_cfg(const double *Am, const double *Xt, double *Ct, int M, int N, int K, cudaStream_t st) {
+    using Cfg = GemmCfg<WM, WN>;
+    if (Cfg::SMEM > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(dense_gemm16_kernel<WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(dense gemm16)");
+    }
+    dim3 grid((M + Cfg::TM - 1) / Cfg::TM, (N + Cfg::TN - 1) / Cfg::TN);
+    dense_gemm16_kernel<WM, WN><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(Am, Xt, Ct, M, N, K);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? IRLB200_OK : fail_cuda(e, "dense_gemm16_kernel");
+}
+
 template <int WM, int WN>
 static int launch_gemm_cfg(const double *Am, const double *Xt, double *Ct, int M, int N, int K, cudaStream_t st) {
     using Cfg = GemmCfg<WM, WN>;
@@ -183,7 +284,9 @@ static int launch_gemm(const double *Am, const double *Xt, double *Ct, int M, in
     // measured at S = 1024, A = 4, B = 4096 (soft-VI sweeps): 64 x 64 tiles 18.4 TFLOP/s, 128 x 128 tiles 17.1 --
     // the small tile's four CTAs per SM hide more latency than the big tile saves in L2 traffic
     if (force == 128) return launch_gemm_cfg<4, 4>(Am, Xt, Ct, M, N, K, st);
-    return launch_gemm_cfg<2, 2>(Am, Xt, Ct, M, N, K, st);
+    if (force == 64) return launch_gemm_cfg<2, 2>(Am, Xt, Ct, M, N, K, st);          // m8n8k4 (sm_80 shape)
+    if (force == 1616) return launch_gemm16_cfg<4, 4>(Am, Xt, Ct, M, N, K, st);      // m16n8k16, 128 x 128 tile
+    return launch_gemm16_cfg<2, 2>(Am, Xt, Ct, M, N, K, st);                         // m16n8k16, 64 x 64 tile
 }
 
 // ---------------------------------------------------------------------------
@@ -197,12 +300,32 @@ struct DenseCtl {
     double *colmax;                   // [B] backward: column maximum of the current sweep
     double *scale;                    // [B] backward: power of two applied to the next sweep
     int *n_active;                    // [1]
+    int *done_now;                    // [B] 1: stopped in the sweep just finalised (consumed by the policy kernel)
 };
 
-__device__ __forceinline__ void vote_diff(const DenseCtl &c, int b, double x_new, double x_old) {
-    const double diff = fabs(x_new - x_old);
-    if (diff != diff) c.nan[b] = 1;
-    else atomicMax(c.delta_bits + b, (unsigned long long)__double_as_longlong(diff));
+// max over the warp of a non-negative double (its bit pattern orders like the value)
+__device__ __forceinline__ double warp_max_nonneg(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// One atomic per warp instead of one per state when the warp's lanes belong to one candidate (always, when
+// S % 32 == 0): S atomics on ONE address per candidate and sweep serialise in L2.  Must be called by full warps.
+__device__ __forceinline__ void vote_diff(const DenseCtl &c, int b, double x_new, double x_old, bool live) {
+    const double diff = live ? fabs(x_new - x_old) : 0.0;
+    const bool nan = diff != diff;
+    const int b0 = __shfl_sync(0xffffffffu, b, 0);
+    if (__all_sync(0xffffffffu, b == b0 || !live)) {
+        const bool any_nan = __any_sync(0xffffffffu, nan);
+        const double m = warp_max_nonneg(nan ? 0.0 : diff);
+        if ((threadIdx.x & 31) == 0) {
+            if (any_nan) c.nan[b0] = 1;
+            atomicMax(c.delta_bits + b0, (unsigned long long)__double_as_longlong(m));
+        }
+    } else if (live) {
+        if (nan) c.nan[b] = 1;
+        else atomicMax(c.delta_bits + b, (unsigned long long)__double_as_longlong(diff));
+    }
 }
 
 // after every sweep, one thread per candidate: `while delta > eps` (NaN ends the loop), max-sweep guard
@@ -220,6 +343,7 @@ __global__ void dense_finalize_kernel(DenseCtl c, int B, double eps, int max_swe
     if (st >= 0) {
         c.status[b] = st;
         c.active[b] = 0;
+        c.done_now[b] = 1;
         atomicSub(c.n_active, 1);
     }
 }
@@ -229,69 +353,103 @@ __global__ void dense_init_ctl_kernel(DenseCtl c, int B) {
     if (b == 0) *c.n_active = B;
     if (b >= B) return;
     c.delta_bits[b] = 0ull; c.nan[b] = 0; c.active[b] = 1; c.n_iter[b] = 0; c.status[b] = IRLB200_ST_CONVERGED;
-    c.colmax[b] = 0.0; c.scale[b] = 1.0;
+    c.colmax[b] = 0.0; c.scale[b] = 1.0; c.done_now[b] = 0;
 }
 
 // ---------------------------------------------------------------------------
 // epilogues (one thread per (candidate, state); T = output of the contraction, candidate-major)
 // ---------------------------------------------------------------------------
 // soft value iteration (maxent.py:329-341) / value iteration (solver.py:44-50): T[b][a*S + s] = P_a[s,:] . x_b
+// q_a and the new value of one (candidate, state) from the contraction's output: the expression tree of
+// phases.cuh::succ_update with dot(a) = t[a * S]
 template <int OP>
-__global__ void dense_succ_epilogue(const double *__restrict__ T, const double *__restrict__ reward,
-                                    const double *__restrict__ phi, double *__restrict__ X, double *__restrict__ policy,
-                                    DenseCtl c, int S, int A, int B, double discount, int vi_mean) {
+__device__ __forceinline__ double dense_succ_value(const double *t, int S, int A, double r, double c1, double discount,
+                                                   int vi_mean, double *q) {
+    for (int a = 0; a < A; ++a) {
+        const double dot = t[(size_t)a * S];
+        q[a] = (OP == kOpSoftVI) ? r + discount * dot : discount * dot;
+    }
+    double xn;
+    if (OP == kOpSoftVI) {
+        double m = c1;
+        for (int a = 0; a < A; ++a) m = max_nan(m, q[a]);
+        if (fabs(m) < INFINITY) {
+            double ssum = 0.0;
+            if (c1 != -INFINITY) ssum = exp(c1 - m);
+            for (int a = 0; a < A; ++a) ssum += exp(q[a] - m);
+            xn = m + log(ssum);
+        } else {
+            xn = c1;
+            for (int a = 0; a < A; ++a) xn = softmax2(xn, q[a]);
+        }
+    } else if (vi_mean) {
+        xn = q[0];
+        for (int a = 1; a < A; ++a) xn += q[a];
+        xn = r + xn / (double)A;
+    } else {
+        xn = q[0];
+        for (int a = 1; a < A; ++a) xn = max_nan(xn, q[a]);
+        xn = r + xn;
+    }
+    return xn;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256)
+    dense_succ_epilogue(const double *__restrict__ T, const double *__restrict__ reward, const double *__restrict__ phi,
+                        double *__restrict__ X, DenseCtl c, int S, int A, int B, double discount, int vi_mean) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = i < (size_t)B * S;
+    const int b = in ? (int)(i / S) : 0, s = in ? (int)(i % S) : 0;
+    const bool live = in && c.active[b];
+    double xn = 0.0, xo = 0.0;
+    if (live) {
+        double q[kMaxDynA];
+        xn = dense_succ_value<OP>(T + (size_t)b * A * S + s, S, A, reward[i], (OP == kOpSoftVI) ? phi[s] : 0.0, discount,
+                                  vi_mean, q);
+        xo = X[i];
+        X[i] = xn;
+    }
+    vote_diff(c, b, xn, xo, live);
+}
+
+// policy of the candidates that stopped in the sweep just finalised (maxent.py:341): q of that sweep (T is still
+// the contraction's output of that sweep) against the value it produced
+__global__ void __launch_bounds__(256)
+    dense_policy_kernel(const double *__restrict__ T, const double *__restrict__ reward, const double *__restrict__ X,
+                        double *__restrict__ policy, DenseCtl c, int S, int A, int B, double discount) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)B * S) return;
     const int b = (int)(i / S), s = (int)(i % S);
-    if (!c.active[b]) return;
-    double q[kMaxDynA];
+    if (!c.done_now[b]) return;
+    const double r = reward[i], x = X[i];
     const double *t = T + (size_t)b * A * S + s;
-    double xn;
-    {
-        const double r = reward[i];
-        const double c1 = (OP == kOpSoftVI) ? phi[s] : 0.0;
-        // same expression tree as phases.cuh::succ_update with dot(a) = t[a * S]
-        for (int a = 0; a < A; ++a) {
-            const double dot = t[(size_t)a * S];
-            q[a] = (OP == kOpSoftVI) ? r + discount * dot : discount * dot;
-        }
-        if (OP == kOpSoftVI) {
-            double m = c1;
-            for (int a = 0; a < A; ++a) m = max_nan(m, q[a]);
-            if (fabs(m) < INFINITY) {
-                double ssum = 0.0;
-                if (c1 != -INFINITY) ssum = exp(c1 - m);
-                for (int a = 0; a < A; ++a) ssum += exp(q[a] - m);
-                xn = m + log(ssum);
-            } else {
-                xn = c1;
-                for (int a = 0; a < A; ++a) xn = softmax2(xn, q[a]);
-            }
-        } else if (vi_mean) {
-            xn = q[0];
-            for (int a = 1; a < A; ++a) xn += q[a];
-            xn = r + xn / (double)A;
-        } else {
-            xn = q[0];
-            for (int a = 1; a < A; ++a) xn = max_nan(xn, q[a]);
-            xn = r + xn;
-        }
-    }
-    vote_diff(c, b, xn, X[i]);
-    X[i] = xn;
-    if (OP == kOpSoftVI && policy)
-        for (int a = 0; a < A; ++a) policy[i * A + a] = exp(q[a] - xn);                    // maxent.py:341
+    for (int a = 0; a < A; ++a) policy[i * A + a] = exp(r + discount * t[(size_t)a * S] - x);
+}
+__global__ void dense_clear_done_kernel(DenseCtl c, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) c.done_now[b] = 0;
 }
 
 // backward sweeps 1 .. n-1 (merged weights): zs' = er * (Pm . zs), times the candidate's power-of-two scale
 __global__ void dense_backward_epilogue(const double *__restrict__ T, const double *__restrict__ reward,
                                         double *__restrict__ X, DenseCtl c, int S, int B) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)B * S) return;
-    const int b = (int)(i / S);
-    const double z = exp(reward[i]) * T[i] * c.scale[b];
-    X[i] = z;
-    if (z == z) atomicMax((unsigned long long *)c.colmax + b, (unsigned long long)__double_as_longlong(fmax(z, 0.0)));
+    const bool in = i < (size_t)B * S;
+    const int b = in ? (int)(i / S) : 0;
+    double z = 0.0;
+    if (in) {
+        z = exp(reward[i]) * T[i] * c.scale[b];
+        X[i] = z;
+    }
+    const double zz = (in && z == z) ? fmax(z, 0.0) : 0.0;
+    const int b0 = __shfl_sync(0xffffffffu, b, 0);
+    if (__all_sync(0xffffffffu, b == b0 || !in)) {
+        const double m = warp_max_nonneg(zz);
+        if ((threadIdx.x & 31) == 0) atomicMax((unsigned long long *)c.colmax + b0, (unsigned long long)__double_as_longlong(m));
+    } else if (in) {
+        atomicMax((unsigned long long *)c.colmax + b, (unsigned long long)__double_as_longlong(zz));
+    }
 }
 __global__ void dense_backward_rescale(DenseCtl c, int B) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -335,12 +493,16 @@ __global__ void dense_svf_prep(const double *__restrict__ policy, const double *
 __global__ void dense_svf_epilogue(const double *__restrict__ T, const double *__restrict__ p0, size_t p0_stride,
                                    double *__restrict__ X, DenseCtl c, int S, int B) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)B * S) return;
-    const int b = (int)(i / S), s = (int)(i % S);
-    if (!c.active[b]) return;
-    const double xn = p0[(size_t)b * p0_stride + s] + T[i];                                 // :110
-    vote_diff(c, b, xn, X[i]);
-    X[i] = xn;
+    const bool in = i < (size_t)B * S;
+    const int b = in ? (int)(i / S) : 0, s = in ? (int)(i % S) : 0;
+    const bool live = in && c.active[b];
+    double xn = 0.0, xo = 0.0;
+    if (live) {
+        xn = p0[(size_t)b * p0_stride + s] + T[i];                                          // :110
+        xo = X[i];
+        X[i] = xn;
+    }
+    vote_diff(c, b, xn, xo, live);
 }
 __global__ void dense_fill_kernel(double *X, size_t n, double v) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -359,7 +521,7 @@ struct DenseWork {
 };
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 static size_t dense_work_bytes_impl(int S, int A, int B) {
-    return 2 * align256(sizeof(double) * (size_t)B * A * S) + 10 * align256(sizeof(double) * (size_t)B) + 256;
+    return 2 * align256(sizeof(double) * (size_t)B * A * S) + 11 * align256(sizeof(double) * (size_t)B) + 256;
 }
 static void carve_work(DenseWork &w, void *work, int S, int A, int B) {
     unsigned char *p = static_cast<unsigned char *>(work);
@@ -371,20 +533,22 @@ static void carve_work(DenseWork &w, void *work, int S, int A, int B) {
     w.c.active = static_cast<int *>(take(8 * (size_t)B));
     w.c.colmax = static_cast<double *>(take(8 * (size_t)B));
     w.c.scale = static_cast<double *>(take(8 * (size_t)B));
+    w.c.done_now = static_cast<int *>(take(8 * (size_t)B));
     w.c.n_iter = static_cast<int32_t *>(take(8 * (size_t)B));          // callers with their own outputs override these
     w.c.status = static_cast<int32_t *>(take(8 * (size_t)B));
     w.c.n_active = static_cast<int *>(take(256));
 }
 
 // run sweeps until no candidate is live; the host looks at the live count every `poll` sweeps
-template <class Sweep>
-static int run_until_done(Sweep sweep, DenseCtl c, int B, double eps, int max_sweeps, cudaStream_t st) {
+template <class Sweep, class After>
+static int run_until_done(Sweep sweep, After after, DenseCtl c, int B, double eps, int max_sweeps, cudaStream_t st) {
     const int poll = 8;
     int live = B;
     for (long long done = 0; live > 0; done += poll) {
         for (int i = 0; i < poll; ++i) {
             if (int rc = sweep()) return rc;
             dense_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(c, B, eps, max_sweeps);
+            after();                                         // what only the candidates that just stopped need
         }
         cudaError_t e = cudaMemcpyAsync(&live, c.n_active, sizeof(int), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -462,11 +626,16 @@ extern "C" int irlb200_dense_batch_succ(int op, const double *packed, int S, int
     dense_fill_kernel<<<blocks, 256, 0, st>>>(value, n, op == 1 ? kNegHuge : 0.0);           // maxent.py:323 / solver.py:29
     auto sweep = [&]() -> int {
         if (int rc = launch_gemm(Pa, value, w.T, A * S, B, S, st)) return rc;
-        if (op == 1) dense_succ_epilogue<kOpSoftVI><<<blocks, 256, 0, st>>>(w.T, reward, phi, value, policy, w.c, S, A, B, discount, 0);
-        else dense_succ_epilogue<kOpVI><<<blocks, 256, 0, st>>>(w.T, reward, nullptr, value, nullptr, w.c, S, A, B, discount, vi_mean);
+        if (op == 1) dense_succ_epilogue<kOpSoftVI><<<blocks, 256, 0, st>>>(w.T, reward, phi, value, w.c, S, A, B, discount, 0);
+        else dense_succ_epilogue<kOpVI><<<blocks, 256, 0, st>>>(w.T, reward, nullptr, value, w.c, S, A, B, discount, vi_mean);
         return IRLB200_OK;
     };
-    return run_until_done(sweep, w.c, B, eps, max_sweeps, st);
+    auto after = [&]() {
+        if (op != 1) return;
+        dense_policy_kernel<<<blocks, 256, 0, st>>>(w.T, reward, value, policy, w.c, S, A, B, discount);
+        dense_clear_done_kernel<<<(B + 127) / 128, 128, 0, st>>>(w.c, B);
+    };
+    return run_until_done(sweep, after, w.c, B, eps, max_sweeps, st);
 }
 
 // expected_svf_from_policy (maxent.py:63-114) for B policies over the shared dense table
@@ -492,7 +661,7 @@ extern "C" int irlb200_dense_batch_svf(const double *packed, int S, int A, int B
         dense_svf_epilogue<<<blocks, 256, 0, st>>>(w.T, p_initial, p0_shared ? 0 : (size_t)S, svf, w.c, S, B);
         return IRLB200_OK;
     };
-    if (int rc = run_until_done(sweep, w.c, B, eps, max_sweeps, st)) return rc;
+    if (int rc = run_until_done(sweep, [] {}, w.c, B, eps, max_sweeps, st)) return rc;
     if (grad) dense_grad_kernel<<<blocks, 256, 0, st>>>(svf, e_features, ef_shared ? 0 : (size_t)S, grad, S, B);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? IRLB200_OK : fail_cuda(e, "dense_batch_svf");
