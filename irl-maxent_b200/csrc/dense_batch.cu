@@ -189,8 +189,8 @@ __global__ void __launch_bounds__(32 * WM * WN, (WM * WN <= 4) ? 4 : 1)
 }
 
 // The same tiling with the 16 x 8 x 16 MMA: per k-chunk of 16 a warp issues 2 x 4 MMAs instead of 64.
-template <int WM, int WN>
-__global__ void __launch_bounds__(32 * WM * WN, (WM * WN <= 4) ? 3 : 1)
+template <int WM, int WN, int MINB>
+__global__ void __launch_bounds__(32 * WM * WN, MINB)
     dense_gemm16_kernel(const double *__restrict__ Am, const double *__restrict__ Xt, double *__restrict__ Ct, int M,
                         int N, int K) {
     using Cfg = GemmCfg<WM, WN>;
@@ -249,15 +249,15 @@ __global__ void __launch_bounds__(32 * WM * WN, (WM * WN <= 4) ? 3 : 1)
             }
 }
 
-template <int WM, int WN>
+template <int WM, int WN, int MINB>
 static int launch_gemm16_cfg(const double *Am, const double *Xt, double *Ct, int M, int N, int K, cudaStream_t st) {
     using Cfg = GemmCfg<WM, WN>;
     if (Cfg::SMEM > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(dense_gemm16_kernel<WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(dense_gemm16_kernel<WM, WN, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
         if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(dense gemm16)");
     }
     dim3 grid((M + Cfg::TM - 1) / Cfg::TM, (N + Cfg::TN - 1) / Cfg::TN);
-    dense_gemm16_kernel<WM, WN><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(Am, Xt, Ct, M, N, K);
+    dense_gemm16_kernel<WM, WN, MINB><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(Am, Xt, Ct, M, N, K);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? IRLB200_OK : fail_cuda(e, "dense_gemm16_kernel");
 }
@@ -285,8 +285,11 @@ static int launch_gemm(const double *Am, const double *Xt, double *Ct, int M, in
     // the small tile's four CTAs per SM hide more latency than the big tile saves in L2 traffic
     if (force == 128) return launch_gemm_cfg<4, 4>(Am, Xt, Ct, M, N, K, st);
     if (force == 64) return launch_gemm_cfg<2, 2>(Am, Xt, Ct, M, N, K, st);          // m8n8k4 (sm_80 shape)
-    if (force == 1616) return launch_gemm16_cfg<4, 4>(Am, Xt, Ct, M, N, K, st);      // m16n8k16, 128 x 128 tile
-    return launch_gemm16_cfg<2, 2>(Am, Xt, Ct, M, N, K, st);                         // m16n8k16, 64 x 64 tile
+    if (force == 1616) return launch_gemm16_cfg<4, 4, 1>(Am, Xt, Ct, M, N, K, st);   // m16n8k16, 128 x 128 tile
+    if (force == 164) return launch_gemm16_cfg<2, 2, 4>(Am, Xt, Ct, M, N, K, st);    // 64 x 64, 4 CTAs per SM (128 registers)
+    if (force == 1642) return launch_gemm16_cfg<4, 2, 2>(Am, Xt, Ct, M, N, K, st);   // 128 x 64, 8 warps, 2 CTAs per SM
+    if (force == 1624) return launch_gemm16_cfg<2, 4, 2>(Am, Xt, Ct, M, N, K, st);   // 64 x 128
+    return launch_gemm16_cfg<2, 2, 3>(Am, Xt, Ct, M, N, K, st);                      // m16n8k16, 64 x 64 tile
 }
 
 // ---------------------------------------------------------------------------
