@@ -299,8 +299,9 @@ int    irlb200_slab_persistent(int op, int rank, int world, void *const *blocks,
 /* Slab mode without a per-sweep barrier (csrc/slab_flow.cu): same arguments and results as
  * irlb200_slab_persistent (blocks of irlb200_slab_flow_block_bytes bytes), but every persistent CTA
  * owns a fixed range of states and waits only for the CTAs (and, on the slab's first / last grid
- * row, the neighbouring GPU's mailbox) within one grid row of it; the stop rule is all-reduced once per `chunk` sweeps (<= 64; <= 0: default 32) and the
- * exact stopping sweep of the reference (maxent.py:108,326; solver.py:40) is reproduced by
+ * row, the neighbouring GPU's mailbox) within one grid row of it; the stop rule is all-reduced once
+ * per `chunk` sweeps (<= 64; <= 0: default, 64 for the forward pass, 32 otherwise) and the exact
+ * stopping sweep of the reference (maxent.py:108,326; solver.py:40) is reproduced by
  * snapshot-and-replay inside the kernel.  Requirement (true for every GridWorld / IcyGridWorld slab): the
  * coupling across a slab boundary is one-to-one and symmetric -- a state s in the first / last `halo` states
  * of a slab links to s -+ halo in the neighbouring slab and to nothing else there, and that state links
