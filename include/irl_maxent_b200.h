@@ -322,6 +322,17 @@ int    irlb200_slab_flow(int op, int rank, int world, void *const *blocks, int S
                          double *out, double *policy_out, int32_t *n_iter, int32_t *status,
                          double timeout_s, int chunk, void *work, size_t work_bytes, void *stream);
 
+/* The same call with dictionary-coded successor probabilities for op 1 / 2: p_code [A][K][cnt] uint8 and p_dict [256]
+ * f64 with p[a][j][i] == p_dict[p_code[a][j][i]] exactly (a grid world's table holds a handful of distinct values);
+ * the sweeps then read one byte per table entry instead of eight -- bitwise the same results.  NULL codes: plain p. */
+int    irlb200_slab_flow_coded(int op, int rank, int world, void *const *blocks, int S_total, int lo, int cnt,
+                               int halo, int A, int K, const int32_t *idx, const double *p,
+                               const uint8_t *p_code, const double *p_dict, const double *c0,
+                               const double *c1, const double *policy_in, const uint8_t *terminal_mask,
+                               double *w_scratch, double discount, double eps, int max_sweeps, int vi_mean,
+                               double *out, double *policy_out, int32_t *n_iter, int32_t *status,
+                               double timeout_s, int chunk, void *work, size_t work_bytes, void *stream);
+
 /* ------------------------------------------------------------------------- *
  * dense feature products on the path: reward = features . theta (maxent.py:244)
  * and grad = e_features - features^T . svf (:248).  features [S][F] row-major.

@@ -73,6 +73,9 @@ SIGNATURES = {
     "irlb200_slab_flow": ([_i, _i, _i, ctypes.POINTER(ctypes.c_void_p), _i, _i, _i, _i, _i, _i, _vp, _vp, _vp,
                            _vp, _vp, _vp, _vp, _d, _d, _i, _i, _vp, _vp, _vp, _vp, _d, _i, _vp, ctypes.c_size_t,
                            _vp], _i),
+    "irlb200_slab_flow_coded": ([_i, _i, _i, ctypes.POINTER(ctypes.c_void_p), _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp,
+                                 _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _vp, _vp, _vp, _vp, _d, _i, _vp,
+                                 ctypes.c_size_t, _vp], _i),
     "irlb200_backward": ([_tp, _i, _vp, _vp, _i, _i, _vp, _i, _vp], _i),
     "irlb200_soft_vi": ([_tp, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _i, _vp], _i),
     "irlb200_value_iteration": ([_tp, _i, _vp, _d, _d, _i, _i, _vp, _vp, _vp, _i, _vp], _i),

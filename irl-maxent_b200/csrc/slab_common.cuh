@@ -61,11 +61,15 @@ struct OverlapArgs {
     double discount, eps;
     int max_sweeps, vi_mean;
     double *out, *policy_out;
+    // optional dictionary-coded successor probabilities (slab_flow.cu, op 1 / 2): p[a][j][i] == dict[code[a][j][i]].
+    // A grid world's table holds a handful of distinct values, so one byte per entry replaces eight.
+    const uint8_t *code;         // [A][K][cnt] or null
+    const double *dict;          // [256]
 };
 
-// one state's update with the iterate read through `xl(global index)`
-template <int OP, int A_T, int K_T, class XL>
-__device__ __forceinline__ double slab_update(const OverlapArgs &a, XL xl, int i, double *q) {
+// one state's update with the iterate read through `xl(global index)` and the table values through `pr(a, j)`
+template <int OP, int A_T, int K_T, class PR, class XL>
+__device__ __forceinline__ double slab_update_p(const OverlapArgs &a, PR pr, XL xl, int i, double *q) {
     const int A = A_T > 0 ? A_T : a.A, K = K_T > 0 ? K_T : a.K;
     if (OP == 3) {
         double acc = 0.0;
@@ -76,9 +80,14 @@ __device__ __forceinline__ double slab_update(const OverlapArgs &a, XL xl, int i
     }
     const double k1 = (OP == kOpSoftVI) ? a.c1[i] : 0.0;
     return succ_update<OP, A_T>(
-        A, K, [&](int aa, int j) { return __ldg(a.p + ((size_t)aa * K + j) * a.cnt + i); },
-        [&](int j) { return xl(__ldg(a.idx + (size_t)j * a.cnt + i)); }, a.c0[i], k1, a.discount,
+        A, K, pr, [&](int j) { return xl(__ldg(a.idx + (size_t)j * a.cnt + i)); }, a.c0[i], k1, a.discount,
         a.vi_mean, q);
+}
+template <int OP, int A_T, int K_T, class XL>
+__device__ __forceinline__ double slab_update(const OverlapArgs &a, XL xl, int i, double *q) {
+    const int K = K_T > 0 ? K_T : a.K;
+    return slab_update_p<OP, A_T, K_T>(
+        a, [&](int aa, int j) { return __ldg(a.p + ((size_t)aa * K + j) * a.cnt + i); }, xl, i, q);
 }
 
 template <int OP, int A_T, int K_T>

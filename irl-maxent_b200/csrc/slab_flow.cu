@@ -62,7 +62,11 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned 
 // U > 1 (forward pass, compile-time K): a thread works on U of its states at a time -- all their table
 // rows are requested first, then all gathers, so a sweep over ~3.5 states per thread (2048 x 2048 on
 // 8 GPUs) is one or two rounds of dependent L2 accesses instead of 3.5.
-template <int OP, int A_T, int K_T, int U, int MINB>
+// CODED (soft-VI / VI): the successor probabilities are read as one byte per entry and decoded through a
+// 256-entry dictionary in shared memory -- bitwise the same doubles, 16 instead of 128 bytes per state and sweep
+// for a 4-action, 4-slot table (2048 x 2048: 168 -> 56 B per state, which turns the sweep from HBM bound into
+// FP64 bound).
+template <int OP, int A_T, int K_T, int U, int MINB, bool CODED = false>
 __global__ void __launch_bounds__(256, MINB)
     slab_flow_kernel(const OverlapArgs a, const SlabPeers pe, unsigned char *base, unsigned long long *progress,
                      double *snap, const int chunk, const int edge, const int res_cap, int32_t *n_iter,
@@ -70,7 +74,12 @@ __global__ void __launch_bounds__(256, MINB)
     extern __shared__ __align__(16) unsigned char res_raw[];   // forward pass: table rows of the CTA's first states
     __shared__ unsigned long long s_gt, s_nanmask;
     __shared__ int s_nan, s_dead;
+    __shared__ double s_dict[CODED ? 256 : 1];
     constexpr int QN = A_T > 0 ? A_T : kMaxDynA;
+    if (CODED) {
+        for (int t = threadIdx.x; t < 256; t += blockDim.x) s_dict[t] = a.dict[t];
+        __syncthreads();
+    }
     SlabShared *sh = reinterpret_cast<SlabShared *>(base);
     FlowShared *fs = reinterpret_cast<FlowShared *>(base + kFlowOffset);
     double *buf0 = reinterpret_cast<double *>(base + kSlabHeaderBytes), *buf1 = buf0 + a.S_total;
@@ -324,7 +333,9 @@ __global__ void __launch_bounds__(256, MINB)
                 }
             } else {
                 for (int i = beg + tid; i < end; i += nthr) {
-                    const double x = slab_update<OP, A_T, K_T>(a, xl, i, nullptr);
+                    const double x = CODED ? slab_update_p<OP, A_T, K_T>(a, [&](int aa, int j) {
+                                                  return s_dict[__ldg(a.code + ((size_t)aa * K + j) * cnt + i)]; }, xl, i, nullptr)
+                                           : slab_update<OP, A_T, K_T>(a, xl, i, nullptr);
                     const double xo = ld_cg(x_in + lo + i);
                     const double diff = fabs(x - xo);
                     gt |= diff > a.eps;
@@ -403,7 +414,10 @@ __global__ void __launch_bounds__(256, MINB)
             a.out[i] = ld_cg(x_new + lo + i);
             if (OP == kOpSoftVI && a.policy_out && q > 0) {
                 double qv[QN];
-                const double x = slab_update<OP, A_T, K_T>(a, [&](int g) { return load_x(x_old, q - 1u, g); }, i, qv);
+                auto xl = [&](int g) { return load_x(x_old, q - 1u, g); };
+                const double x = CODED ? slab_update_p<OP, A_T, K_T>(a, [&](int aa, int j) {
+                                              return s_dict[__ldg(a.code + ((size_t)aa * K + j) * cnt + i)]; }, xl, i, qv)
+                                       : slab_update<OP, A_T, K_T>(a, xl, i, qv);
                 for (int aa = 0; aa < A; ++aa) a.policy_out[(size_t)i * A + aa] = exp(qv[aa] - x);     // maxent.py:341
             }
         }
@@ -453,6 +467,18 @@ extern "C" int irlb200_slab_flow(int op, int rank, int world, void *const *block
                                  double *w_scratch, double discount, double eps, int max_sweeps, int vi_mean,
                                  double *out, double *policy_out, int32_t *n_iter, int32_t *status, double timeout_s,
                                  int chunk, void *work, size_t work_bytes, void *stream) {
+    return irlb200_slab_flow_coded(op, rank, world, blocks, S_total, lo, cnt, halo, A, K, idx, p, nullptr, nullptr, c0, c1,
+                                   policy_in, terminal_mask, w_scratch, discount, eps, max_sweeps, vi_mean, out,
+                                   policy_out, n_iter, status, timeout_s, chunk, work, work_bytes, stream);
+}
+
+extern "C" int irlb200_slab_flow_coded(int op, int rank, int world, void *const *blocks, int S_total, int lo, int cnt,
+                                       int halo, int A, int K, const int32_t *idx, const double *p,
+                                       const uint8_t *p_code, const double *p_dict, const double *c0,
+                                       const double *c1, const double *policy_in, const uint8_t *terminal_mask,
+                                       double *w_scratch, double discount, double eps, int max_sweeps, int vi_mean,
+                                       double *out, double *policy_out, int32_t *n_iter, int32_t *status,
+                                       double timeout_s, int chunk, void *work, size_t work_bytes, void *stream) {
     if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world || !blocks || cnt <= 0 || halo <= 0 || !idx || !p ||
         !c0 || !out || !work)
         return fail(IRLB200_EINVAL, "slab_flow: bad argument");
@@ -475,6 +501,8 @@ extern "C" int irlb200_slab_flow(int op, int rank, int world, void *const *block
     oa.idx = idx; oa.p = p; oa.c0 = c0; oa.c1 = c1; oa.policy_in = policy_in; oa.term = terminal_mask;
     oa.w = w_scratch; oa.discount = discount; oa.eps = eps; oa.max_sweeps = max_sweeps; oa.vi_mean = vi_mean;
     oa.out = out; oa.policy_out = policy_out;
+    const bool coded = p_code && p_dict && op != 3 && A == 4 && (K == 4 || K == 5) && flow_env_int("IRLB200_FLOW_CODED", 1);
+    oa.code = coded ? p_code : nullptr; oa.dict = coded ? p_dict : nullptr;
 
     const bool fast = (A == 4 && K == 5), compact = (A == 4 && K == 4);
     const void *k = nullptr;
@@ -487,11 +515,17 @@ extern "C" int irlb200_slab_flow(int op, int rank, int world, void *const *block
                     : fwd == 23 ? (const void *)slab_flow_kernel<3, 4, 4, 2, 3> : (const void *)slab_flow_kernel<3, 4, 4, 2, 4>;
         else k = (const void *)slab_flow_kernel<3, 0, 0, 1, 4>;
     } else if (op == 1) {
-        k = fast ? (const void *)slab_flow_kernel<kOpSoftVI, 4, 5, 1, 3> : compact ? (const void *)slab_flow_kernel<kOpSoftVI, 4, 4, 1, 3>
-                 : (const void *)slab_flow_kernel<kOpSoftVI, 0, 0, 1, 3>;
+        // coded rows: the sweep is FP64 bound (exp / log), and four CTAs of 256 threads per SM (64 registers, a small
+        // spill) hide its latencies better than three: 53.2 -> 47.0 us per sweep at 2.1 M states (2: 59.7)
+        const int occ = flow_env_int("IRLB200_FLOW_SOFTVI_OCC", 4);
+        if (coded && occ == 4) k = fast ? (const void *)slab_flow_kernel<kOpSoftVI, 4, 5, 1, 4, true> : (const void *)slab_flow_kernel<kOpSoftVI, 4, 4, 1, 4, true>;
+        else if (coded) k = fast ? (const void *)slab_flow_kernel<kOpSoftVI, 4, 5, 1, 3, true> : (const void *)slab_flow_kernel<kOpSoftVI, 4, 4, 1, 3, true>;
+        else k = fast ? (const void *)slab_flow_kernel<kOpSoftVI, 4, 5, 1, 3> : compact ? (const void *)slab_flow_kernel<kOpSoftVI, 4, 4, 1, 3>
+                      : (const void *)slab_flow_kernel<kOpSoftVI, 0, 0, 1, 3>;
     } else {
-        k = fast ? (const void *)slab_flow_kernel<kOpVI, 4, 5, 1, 3> : compact ? (const void *)slab_flow_kernel<kOpVI, 4, 4, 1, 3>
-                 : (const void *)slab_flow_kernel<kOpVI, 0, 0, 1, 3>;
+        if (coded) k = fast ? (const void *)slab_flow_kernel<kOpVI, 4, 5, 1, 3, true> : (const void *)slab_flow_kernel<kOpVI, 4, 4, 1, 3, true>;
+        else k = fast ? (const void *)slab_flow_kernel<kOpVI, 4, 5, 1, 3> : compact ? (const void *)slab_flow_kernel<kOpVI, 4, 4, 1, 3>
+                      : (const void *)slab_flow_kernel<kOpVI, 0, 0, 1, 3>;
     }
 
     const int threads = 256;

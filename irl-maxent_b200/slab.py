@@ -261,6 +261,18 @@ class PeerSlabGrid(SlabGrid):
         self.flow = int(os.environ.get("IRLB200_SLAB_FLOW", "1" if flow else "0"))
         self.chunk_sweeps = int(chunk_sweeps)
         self._work = None
+        # dictionary-coded successor probabilities for the soft-VI / VI sweeps of the dataflow kernel: a grid world's
+        # table holds a handful of distinct values, so the sweeps read one byte per entry instead of eight
+        self._code, self._dict = None, None
+        if self.flow and os.environ.get("IRLB200_FLOW_CODED", "1") != "0":
+            torch = self.torch
+            sp = self.tables["succ_p"]
+            vals = torch.unique(sp)
+            if 0 < vals.numel() <= 256:
+                self._code = torch.searchsorted(vals, sp.reshape(-1)).to(torch.uint8).reshape(sp.shape).contiguous()
+                self._dict = torch.zeros(256, dtype=torch.float64, device=sp.device)
+                self._dict[:vals.numel()] = vals
+                assert bool((self._dict[self._code.long()] == sp).all()), "dictionary coding must be exact"
         import ctypes
         E = self.backend.E
         self.E, self.ct = E, ctypes
@@ -321,9 +333,11 @@ class PeerSlabGrid(SlabGrid):
                 if self._work is None:
                     nbytes = int(E._lib.irlb200_slab_flow_work_bytes(self.cnt))
                     self._work = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-                E._check(E._lib.irlb200_slab_flow(
+                coded = op != OP_SVF and self._code is not None
+                E._check(E._lib.irlb200_slab_flow_coded(
                     op, self.rank, self.world, self._blocks, self.n_states, self.lo, self.cnt, self.halo, self.A,
-                    self.K, E._ptr(idx), E._ptr(p), E._ptr(c0), E._ptr(c1), E._ptr(policy_in), E._ptr(mask),
+                    self.K, E._ptr(idx), E._ptr(p), E._ptr(self._code if coded else None),
+                    E._ptr(self._dict if coded else None), E._ptr(c0), E._ptr(c1), E._ptr(policy_in), E._ptr(mask),
                     E._ptr(w_scratch), float(discount), float(eps), ms, int(vi_mean), E._ptr(out), E._ptr(policy_out),
                     E._ptr(n_iter), E._ptr(status), self.timeout_s, self.chunk_sweeps, E._ptr(self._work),
                     self._work.numel(), E._stream()))
